@@ -1,0 +1,287 @@
+#include "conv_igemm.cuh"
+
+#include <cstdio>
+#include <cstring>
+
+#include "ptx.cuh"
+
+namespace vgh {
+
+static thread_local char g_conv_err[256] = "";
+const char* conv_last_error() { return g_conv_err; }
+
+constexpr int kBlockM = 128;
+constexpr int kThreads = 192;  // warp0 TMA, warp1 MMA/TMEM, warps 2..5 epilogue
+
+template <int BK>
+__global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvLaunch p) {
+  constexpr uint32_t kRowBytes = BK * 2;            // bytes of one K-slab row == swizzle span
+  constexpr uint32_t kABytes = kBlockM * kRowBytes;  // A stage
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_bytes = static_cast<uint32_t>(p.block_n) * kRowBytes;
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = a_base + p.stages * kABytes;
+  const uint32_t bar_base = b_base + p.stages * b_bytes;  // 8-byte aligned (multiples of 1024)
+  const uint32_t full_bar = bar_base;                     // [stages]
+  const uint32_t empty_bar = bar_base + 8 * p.stages;     // [stages]
+  const uint32_t tmem_full_bar = bar_base + 16 * p.stages;
+  const uint32_t tmem_slot = tmem_full_bar + 8;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- tile coordinates
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int b_img = blockIdx.x / tiles_per_img;
+  const int t_in = blockIdx.x - b_img * tiles_per_img;
+  const int tyi = t_in / p.tiles_x;
+  const int h0 = tyi * p.th;
+  const int w0 = (t_in - tyi * p.tiles_x) * p.tw;
+  const int n0 = blockIdx.y * p.block_n;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_dyn(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_acc;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_acc) : "r"(tmem_slot));
+
+  const int cblks = p.cin / BK;
+  const int num_kb = p.ntaps * cblks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      const uint32_t tx_bytes = static_cast<uint32_t>(p.tw * p.th) * kRowBytes + b_bytes;
+      int stage = 0;
+      uint32_t phase = 0;
+      int tap = 0, cb = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+        const uint32_t fb = full_bar + 8 * stage;
+        mbar_arrive_expect_tx(fb, tx_bytes);
+        const int ty = tap / p.kw;
+        const int tx = tap - ty * p.kw;
+        tma_load_4d(a_base + stage * kABytes, &p.tmA, fb, p.cin_off + cb * BK, w0 * p.stride + tx - p.pad,
+                    h0 * p.stride + ty - p.pad, b_img);
+        tma_load_2d(b_base + stage * b_bytes, &p.tmB, fb, tap * p.cin + cb * BK, n0);
+        if (++cb == cblks) {
+          cb = 0;
+          ++tap;
+        }
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer (one thread) =====================
+      const uint32_t idesc = umma_idesc_bf16(kBlockM, static_cast<uint32_t>(p.block_n));
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar + 8 * stage, phase);
+        tc_fence_after();
+        const uint64_t a_desc = umma_smem_desc(a_base + stage * kABytes, kRowBytes);
+        const uint64_t b_desc = umma_smem_desc(b_base + stage * b_bytes, kRowBytes);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // advance 16 elements (32 B) along K inside the swizzle span: +2 in 16-byte units
+          umma_bf16(tmem_acc, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(empty_bar + 8 * stage);  // frees the smem slot once these MMAs retire
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
+    const int r = quarter * 32 + lane;
+    const int ly = r / p.tw;
+    const int lx = r - ly * p.tw;
+    const int oh = h0 + ly, ow = w0 + lx;
+    const bool row_ok = (r < p.tw * p.th) && (oh < p.Ho) && (ow < p.Wo);
+
+    int n_shift = 0;  // channel shift when the n-tile addresses a sub-pixel of the 2x2 transpose conv
+    int ph = oh, pw = ow;
+    if (p.up) {
+      const int sub = n0 / p.up_cout;
+      n_shift = sub * p.up_cout;
+      ph = 2 * oh + (sub >> 1);
+      pw = 2 * ow + (sub & 1);
+    }
+    const size_t out_pix = (static_cast<size_t>(b_img) * p.out_H + ph) * p.out_W + pw;
+    const size_t out_off = out_pix * p.out_cstride + p.out_coff + (n0 - n_shift);
+    const size_t res_off =
+        ((static_cast<size_t>(b_img) * p.Ho + oh) * p.Wo + ow) * p.res_cstride + p.res_coff + n0;
+
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
+    const int n_chunks = p.block_n >> 4;
+    for (int c = 0; c < n_chunks; ++c) {
+      uint32_t v[16];
+      tmem_ld16(taddr + c * 16, v);
+      tmem_ld_wait();
+      const int n = n0 + c * 16;
+      if (!row_ok || n >= p.n_total) continue;
+      float f[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float x = __uint_as_float(v[i]) + __ldg(p.bias + n + i);
+        f[i] = p.relu ? fmaxf(x, 0.f) : x;
+      }
+      if (p.res != nullptr) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.res + res_off + c * 16);
+        uint4 q0 = __ldg(rp), q1 = __ldg(rp + 1);
+        const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+          f[2 * i] = fmaf(p.res_alpha, __bfloat162float(h.x), f[2 * i]);
+          f[2 * i + 1] = fmaf(p.res_alpha, __bfloat162float(h.y), f[2 * i + 1]);
+        }
+      }
+      if (p.out_fp32) {
+        float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + out_off + c * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+      } else {
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+          w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + out_off + c * 16);
+        op[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        op[1] = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_dyn(tmem_acc, static_cast<uint32_t>(p.tmem_cols));
+  }
+}
+
+// ------------------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || ptr == nullptr) {
+    snprintf(g_conv_err, sizeof(g_conv_err), "cuTensorMapEncodeTiled unavailable (%s)", cudaGetErrorString(e));
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  return fn;
+}
+
+int conv_pick_stages(int block_n, int bk) {
+  const int stage = (kBlockM + block_n) * bk * 2;
+  int s = (104 * 1024) / stage;  // two CTAs per SM: the second CTA's main loop hides this one's epilogue
+  if (s < 2) s = 2;
+  if (s > 8) s = 8;
+  return s;
+}
+
+size_t conv_smem_bytes(const ConvLaunch& L, int bk) {
+  return 1024 + static_cast<size_t>(L.stages) * (kBlockM + L.block_n) * bk * 2 + 16 * L.stages + 16;
+}
+
+int conv_make_tensor_maps(ConvLaunch& L, const void* in_base, int in_C, int in_H, int in_W, const void* w_base,
+                          int k_total, int n_pad, int bk) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return 1;
+  const CUtensorMapSwizzle sw = bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)in_C, (cuuint64_t)in_W, (cuuint64_t)in_H, (cuuint64_t)L.B};
+    cuuint64_t strides[3] = {(cuuint64_t)in_C * 2, (cuuint64_t)in_W * in_C * 2, (cuuint64_t)in_H * in_W * in_C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(L.tw * L.stride), (cuuint32_t)(L.th * L.stride), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)L.stride, (cuuint32_t)L.stride, 1};
+    CUresult r = enc(&L.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in_base), dims, strides, box,
+                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      snprintf(g_conv_err, sizeof(g_conv_err), "encode A map failed: %d (C=%d W=%d H=%d B=%d box %d,%d,%d s=%d)", (int)r,
+               in_C, in_W, in_H, L.B, bk, L.tw, L.th, L.stride);
+      return 2;
+    }
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)n_pad};
+    cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
+    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)L.block_n};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&L.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      snprintf(g_conv_err, sizeof(g_conv_err), "encode B map failed: %d (K=%d N=%d box %d,%d)", (int)r, k_total, n_pad,
+               bk, L.block_n);
+      return 3;
+    }
+  }
+  return 0;
+}
+
+template <int BK>
+static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
+  static size_t configured = 0;
+  const size_t smem = conv_smem_bytes(L, BK);
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      snprintf(g_conv_err, sizeof(g_conv_err), "set smem %zu failed: %s", smem, cudaGetErrorString(e));
+      return 4;
+    }
+    configured = smem;
+  }
+  dim3 grid(L.tiles_x * L.tiles_y * L.B, (L.n_total + L.block_n - 1) / L.block_n);
+  conv_igemm_kernel<BK><<<grid, kThreads, smem, stream>>>(L);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(g_conv_err, sizeof(g_conv_err), "conv launch failed: %s", cudaGetErrorString(e));
+    return 5;
+  }
+  return 0;
+}
+
+int conv_launch(const ConvLaunch& L, int bk, cudaStream_t stream) {
+  if (bk == 64) return launch_t<64>(L, stream);
+  if (bk == 32) return launch_t<32>(L, stream);
+  snprintf(g_conv_err, sizeof(g_conv_err), "unsupported BK %d", bk);
+  return 6;
+}
+
+}  // namespace vgh

@@ -1,0 +1,48 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a), NHWC bf16 activations.
+//
+//   D[pixel, cout] = sum_{tap, cin} A[pixel shifted by tap, cin] * W[cout, tap, cin]   (+bias, ReLU, +alpha*res)
+//
+// One CTA = one 128-pixel x BLOCK_N output tile.  The 128 "GEMM rows" are a th x tw rectangle of
+// output pixels of one image; for every filter tap the matching input rectangle is fetched by ONE
+// 4-D TMA box (channels innermost, 128B/64B swizzle) whose out-of-bounds part is zero-filled by the
+// TMA unit - that is the convolution padding, and stride-2 layers use the tensor map's traversal
+// stride.  No im2col buffer exists anywhere.  Weights are pre-packed K-major [Cout_pad][taps*Cin]
+// and fetched by a 2-D TMA box.  Warp roles: warp0 = TMA producer, warp1 = TMEM owner + MMA issuer
+// (single thread), warps 2..5 = epilogue (tcgen05.ld -> bias/ReLU/residual -> global stores into
+// a channel slice of the consumer's buffer, optionally pixel-shuffled for the 2x2 conv-transpose).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace vgh {
+
+struct ConvLaunch {
+  CUtensorMap tmA;  // input  [C_total, W, H, B] bf16 (innermost first)
+  CUtensorMap tmB;  // weights [K_total, N_pad]  bf16
+  const float* bias;             // [N_pad]
+  void* out;                     // output buffer base (bf16 or fp32)
+  const __nv_bfloat16* res;      // residual buffer base or nullptr
+  int B, Ho, Wo;                 // GEMM-row space: output pixels (before any pixel shuffle)
+  int tw, th, tiles_x, tiles_y;  // spatial tile (tw*th <= 128) and tile counts per image
+  int cin_off, cin;              // channel coordinate offset / channels per tap (multiple of BK)
+  int ntaps, kw, stride, pad;    // filter taps (kh*kw), kw, conv stride, padding
+  int n_total, block_n;          // stored output channels (multiple of 16), UMMA N of this launch
+  int out_cstride, out_coff, out_H, out_W;
+  int up, up_cout;               // up=1: conv-transpose 2x2/s2, n-tile -> sub-pixel (n / up_cout)
+  int relu, out_fp32;
+  int res_cstride, res_coff;
+  float res_alpha;
+  int stages, tmem_cols;
+};
+
+// Host side (conv_igemm.cu)
+int conv_make_tensor_maps(ConvLaunch& L, const void* in_base, int in_C, int in_H, int in_W, const void* w_base,
+                          int k_total, int n_pad, int bk);
+int conv_launch(const ConvLaunch& L, int bk, cudaStream_t stream);
+size_t conv_smem_bytes(const ConvLaunch& L, int bk);
+int conv_pick_stages(int block_n, int bk);
+const char* conv_last_error();
+
+}  // namespace vgh

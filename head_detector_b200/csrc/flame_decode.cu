@@ -1,0 +1,402 @@
+// Fused FLAME decode for sm_100a: 413-float head parameters -> 5023x3 vertices.
+//
+// Replaces the reference's ~25 library launches per call (head_detector/flame.py:122-169 ->
+// smplx.lbs.lbs; flame.py:179-208; utils.py:120-128; detector.py:66-69) with ONE kernel:
+//   blendshapes (shape+expression) -> jaw pose correctives -> joint regression -> LBS skinning
+//   -> +0.05 z -> 6D rotation -> scale -> translate -> un-letterbox.
+//
+// Precision contract (DESIGN.md "FLAME decode"): everything up to the model-space vertex is
+// accumulated in fp64 (the reference's own fp32 rounding is the only difference left), the vertex
+// is rounded once to fp32, and the remaining ops (R*v, *scale, +t, -pad, /scale) are done in fp32
+// in the reference's operation order with non-contracted intrinsics so that roundings coincide.
+//
+// Work decomposition: CTA = 128 vertices x (8*HG heads).  Each thread owns one vertex (3 coords) for
+// 8 heads = 24 fp64 accumulators.  The shape basis slab of the CTA's 128 vertices streams through a
+// double-buffered cp.async pipeline (8 coefficients per stage) and is shared by the HG head groups;
+// betas live in shared memory as fp64 and are read as broadcast 128-bit loads.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "flame_decode.cuh"
+
+namespace vgh {
+
+constexpr int kV = 5023;
+constexpr int kVPad = 5120;  // 40 tiles of 128 vertices; padded rows are zero
+constexpr int kL = 400;
+constexpr int kTileV = 128;
+constexpr int kHPT = 8;   // heads per thread
+constexpr int kLc = 8;    // coefficients per pipeline stage
+constexpr int kNPose = 9; // live pose-corrective rows (jaw joint only)
+constexpr int kParams = 413;
+
+struct FlameDev {
+  double* sdt;   // [400][kVPad][3]  shape basis, coefficient-major
+  double* pd;    // [9][kVPad][3]    posedirs rows 9..17 (jaw)
+  double* vt;    // [kVPad][3]       template
+  double* wI;    // [kVPad]          W0+W1+W3+W4
+  double* w2;    // [kVPad]          W2 (jaw)
+  double* js2;   // [3][400]         J_regressor[2] . shapedirs
+  double j2t[3]; //                  J_regressor[2] . v_template
+};
+
+struct FlameArgs {
+  FlameDev c;
+  const float* params;  // [N,413]
+  const float* xform;   // [N,3] (pad_x, pad_y, img_scale) or null
+  const int* n_dev;     // optional device-side head count (overrides n when non-null)
+  float* verts;         // optional [N,5023,3] model space (incl. +0.05 z)
+  float* rot;           // optional [N,9]
+  float* proj;          // [N,5023,3]
+  int n;
+  int ns, ne;           // live shape / expression coefficient counts
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// rot6d -> rotation matrix, reference op order (utils.py:120-128; F.normalize eps 1e-12), fp32.
+__device__ void rot6d_to_mat(const float* v, float* R /*row-major 3x3*/) {
+  float n1 = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(v[0], v[0]), __fmul_rn(v[1], v[1])), __fmul_rn(v[2], v[2])));
+  n1 = fmaxf(n1, 1e-12f);
+  float b1[3] = {__fdiv_rn(v[0], n1), __fdiv_rn(v[1], n1), __fdiv_rn(v[2], n1)};
+  const float* vy = v + 3;
+  float c[3] = {__fsub_rn(__fmul_rn(b1[1], vy[2]), __fmul_rn(b1[2], vy[1])),
+                __fsub_rn(__fmul_rn(b1[2], vy[0]), __fmul_rn(b1[0], vy[2])),
+                __fsub_rn(__fmul_rn(b1[0], vy[1]), __fmul_rn(b1[1], vy[0]))};
+  float n3 = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(c[0], c[0]), __fmul_rn(c[1], c[1])), __fmul_rn(c[2], c[2])));
+  n3 = fmaxf(n3, 1e-12f);
+  float b3[3] = {__fdiv_rn(c[0], n3), __fdiv_rn(c[1], n3), __fdiv_rn(c[2], n3)};
+  float b2[3] = {-__fsub_rn(__fmul_rn(b1[1], b3[2]), __fmul_rn(b1[2], b3[1])),
+                 -__fsub_rn(__fmul_rn(b1[2], b3[0]), __fmul_rn(b1[0], b3[2])),
+                 -__fsub_rn(__fmul_rn(b1[0], b3[1]), __fmul_rn(b1[1], b3[0]))};
+  // columns are (b1, b2, b3)
+  for (int i = 0; i < 3; ++i) {
+    R[i * 3 + 0] = b1[i];
+    R[i * 3 + 1] = b2[i];
+    R[i * 3 + 2] = b3[i];
+  }
+}
+
+// Rodrigues as smplx.lbs.batch_rodrigues does it in fp32: angle = |r + 1e-8|, axis = r / angle.
+__device__ void rodrigues_f32(const float* r, float* R) {
+  float a0 = __fadd_rn(r[0], 1e-8f), a1 = __fadd_rn(r[1], 1e-8f), a2 = __fadd_rn(r[2], 1e-8f);
+  float ang = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(a0, a0), __fmul_rn(a1, a1)), __fmul_rn(a2, a2)));
+  float kx = __fdiv_rn(r[0], ang), ky = __fdiv_rn(r[1], ang), kz = __fdiv_rn(r[2], ang);
+  float s = sinf(ang), c = cosf(ang);
+  float K[9] = {0.f, -kz, ky, kz, 0.f, -kx, -ky, kx, 0.f};
+  float KK[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      float acc = __fmul_rn(K[i * 3 + 0], K[0 * 3 + j]);
+      acc = __fmaf_rn(K[i * 3 + 1], K[1 * 3 + j], acc);
+      acc = __fmaf_rn(K[i * 3 + 2], K[2 * 3 + j], acc);
+      KK[i * 3 + j] = acc;
+    }
+  float omc = __fsub_rn(1.f, c);
+  for (int i = 0; i < 9; ++i) {
+    float id = (i == 0 || i == 4 || i == 8) ? 1.f : 0.f;
+    R[i] = __fadd_rn(__fadd_rn(id, __fmul_rn(s, K[i])), __fmul_rn(omc, KK[i]));
+  }
+}
+
+template <int HG>
+__global__ void __launch_bounds__(kTileV* HG) flame_decode_kernel(const FlameArgs a) {
+  constexpr int kHeads = kHPT * HG;
+  const int n_heads = a.n_dev ? min(*a.n_dev, a.n) : a.n;
+  const int head0 = blockIdx.y * kHeads;
+  if (head0 >= n_heads) return;
+  const int v0 = blockIdx.x * kTileV;
+  const int tid = threadIdx.x;
+  const int vl = tid % kTileV;
+  const int grp = tid / kTileV;
+  const int lb = a.ns + a.ne;          // live blendshape coefficients
+  const int lt = lb + kNPose;          // + pose-corrective rows
+  const int n_chunks = (lt + kLc - 1) / kLc;
+  const int lt_pad = n_chunks * kLc;
+
+  extern __shared__ __align__(16) uint8_t smem[];
+  double* sd_s = reinterpret_cast<double*>(smem);                       // [2][kLc][128][3]
+  double* beta_s = sd_s + 2 * kLc * kTileV * 3;                         // [lt_pad][kHeads]
+  double* tj_s = beta_s + static_cast<size_t>(lt_pad) * kHeads;         // [kHeads][3]
+  double* r2_s = tj_s + kHeads * 3;                                     // [kHeads][9]
+  float* R_s = reinterpret_cast<float*>(r2_s + kHeads * 9);             // [kHeads][9]
+  float* st_s = R_s + kHeads * 9;                                       // [kHeads][8]: scale,tx,ty,tz,padx,pady,iscale
+
+  // ---- prologue: betas (fp64), per-head rotations
+  for (int idx = tid; idx < lb * kHeads; idx += blockDim.x) {
+    const int h = idx / lb, i = idx - h * lb;
+    const int l = i < a.ns ? i : 300 + (i - a.ns);
+    const int hg = head0 + h;
+    beta_s[i * kHeads + h] = hg < n_heads ? static_cast<double>(a.params[static_cast<size_t>(hg) * kParams + l]) : 0.0;
+  }
+  for (int idx = tid; idx < (lt_pad - lt) * kHeads; idx += blockDim.x) beta_s[lt * kHeads + idx] = 0.0;
+  if (tid < kHeads) {
+    const int hg = head0 + tid;
+    float R2[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    float sc = 1.f, t[3] = {0, 0, 0}, xf[3] = {0.f, 0.f, 1.f};
+    if (hg < n_heads) {
+      const float* p = a.params + static_cast<size_t>(hg) * kParams;
+      rodrigues_f32(p + 400, R2);
+      rot6d_to_mat(p + 403, R);
+      t[0] = p[409]; t[1] = p[410]; t[2] = p[411];
+      sc = fmaxf(p[412], 1e-8f);
+      if (a.xform) { xf[0] = a.xform[hg * 3]; xf[1] = a.xform[hg * 3 + 1]; xf[2] = a.xform[hg * 3 + 2]; }
+      if (a.rot && blockIdx.x == 0)
+        for (int i = 0; i < 9; ++i) a.rot[static_cast<size_t>(hg) * 9 + i] = R[i];
+    }
+    for (int i = 0; i < 9; ++i) {
+      r2_s[tid * 9 + i] = static_cast<double>(R2[i]);
+      R_s[tid * 9 + i] = R[i];
+      // pose feature = (R2 - I) in fp32, as the reference forms it, acts as 9 extra "betas"
+      const float id = (i == 0 || i == 4 || i == 8) ? 1.f : 0.f;
+      beta_s[(lb + i) * kHeads + tid] = static_cast<double>(__fsub_rn(R2[i], id));
+    }
+    st_s[tid * 8 + 0] = sc; st_s[tid * 8 + 1] = t[0]; st_s[tid * 8 + 2] = t[1]; st_s[tid * 8 + 3] = t[2];
+    st_s[tid * 8 + 4] = xf[0]; st_s[tid * 8 + 5] = xf[1]; st_s[tid * 8 + 6] = xf[2];
+  }
+  __syncthreads();
+  // jaw joint J2 = J2_template + JS2 . beta ; tJ = J2 - R2 . J2
+  if (tid < kHeads * 3) {
+    const int h = tid / 3, k = tid - h * 3;
+    double acc = a.c.j2t[k];
+    for (int i = 0; i < lb; ++i) {
+      const int l = i < a.ns ? i : 300 + (i - a.ns);
+      acc = fma(a.c.js2[k * kL + l], beta_s[i * kHeads + h], acc);
+    }
+    tj_s[tid] = acc;  // temporarily J2
+  }
+  __syncthreads();
+  if (tid < kHeads) {
+    const double j0 = tj_s[tid * 3], j1 = tj_s[tid * 3 + 1], j2 = tj_s[tid * 3 + 2];
+    const double* r = r2_s + tid * 9;
+    const double o0 = j0 - (r[0] * j0 + r[1] * j1 + r[2] * j2);
+    const double o1 = j1 - (r[3] * j0 + r[4] * j1 + r[5] * j2);
+    const double o2 = j2 - (r[6] * j0 + r[7] * j1 + r[8] * j2);
+    tj_s[tid * 3] = o0; tj_s[tid * 3 + 1] = o1; tj_s[tid * 3 + 2] = o2;
+  }
+  // (visibility of tj_s to everyone is guaranteed by the __syncthreads inside the main loop)
+
+  // ---- main loop: acc[h][k] = template + sum_i beta[h][i] * basis[i][v][k]
+  double acc[kHPT][3];
+  {
+    const double t0 = a.c.vt[(v0 + vl) * 3], t1 = a.c.vt[(v0 + vl) * 3 + 1], t2 = a.c.vt[(v0 + vl) * 3 + 2];
+#pragma unroll
+    for (int h = 0; h < kHPT; ++h) { acc[h][0] = t0; acc[h][1] = t1; acc[h][2] = t2; }
+  }
+  const uint32_t sd_smem = static_cast<uint32_t>(__cvta_generic_to_shared(sd_s));
+  constexpr int kRowBytes = kTileV * 3 * 8;            // 3072 B per coefficient row
+  constexpr int kStageBytes = kLc * kRowBytes;         // 24576 B
+  constexpr int kVecPerStage = kStageBytes / 16;       // 1536
+  auto issue = [&](int chunk, int buf) {
+    for (int q = tid; q < kVecPerStage; q += blockDim.x) {
+      const int row = q / (kRowBytes / 16);
+      const int off = q - row * (kRowBytes / 16);
+      int i = chunk * kLc + row;
+      const double* src;
+      if (i < lb) {
+        const int l = i < a.ns ? i : 300 + (i - a.ns);
+        src = a.c.sdt + (static_cast<size_t>(l) * kVPad + v0) * 3;
+      } else {
+        const int m = min(i - lb, kNPose - 1);  // rows past the end multiply a zero beta
+        src = a.c.pd + (static_cast<size_t>(m) * kVPad + v0) * 3;
+      }
+      cp_async16(sd_smem + buf * kStageBytes + row * kRowBytes + off * 16, reinterpret_cast<const uint8_t*>(src) + off * 16);
+    }
+    cp_async_commit();
+  };
+  issue(0, 0);
+  for (int c = 0; c < n_chunks; ++c) {
+    if (c + 1 < n_chunks) {
+      issue(c + 1, (c + 1) & 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const double* sd = sd_s + (c & 1) * (kLc * kTileV * 3) + vl * 3;
+    const double* bt = beta_s + static_cast<size_t>(c) * kLc * kHeads + grp * kHPT;
+#pragma unroll
+    for (int r = 0; r < kLc; ++r) {
+      const double s0 = sd[r * kTileV * 3], s1 = sd[r * kTileV * 3 + 1], s2 = sd[r * kTileV * 3 + 2];
+      const double2* b2 = reinterpret_cast<const double2*>(bt + r * kHeads);
+#pragma unroll
+      for (int hh = 0; hh < kHPT / 2; ++hh) {
+        const double2 b = b2[hh];
+        acc[2 * hh][0] = fma(s0, b.x, acc[2 * hh][0]);
+        acc[2 * hh][1] = fma(s1, b.x, acc[2 * hh][1]);
+        acc[2 * hh][2] = fma(s2, b.x, acc[2 * hh][2]);
+        acc[2 * hh + 1][0] = fma(s0, b.y, acc[2 * hh + 1][0]);
+        acc[2 * hh + 1][1] = fma(s1, b.y, acc[2 * hh + 1][1]);
+        acc[2 * hh + 1][2] = fma(s2, b.y, acc[2 * hh + 1][2]);
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue: skinning + rigid transform, per head
+  const int v = v0 + vl;
+  if (v >= kV) return;
+  const double wi = a.c.wI[v], w2 = a.c.w2[v];
+#pragma unroll
+  for (int h = 0; h < kHPT; ++h) {
+    const int hl = grp * kHPT + h;
+    const int hg = head0 + hl;
+    if (hg >= n_heads) break;
+    const double* r2 = r2_s + hl * 9;
+    const double x = acc[h][0], y = acc[h][1], z = acc[h][2];
+    const double rx = r2[0] * x + r2[1] * y + r2[2] * z + tj_s[hl * 3];
+    const double ry = r2[3] * x + r2[4] * y + r2[5] * z + tj_s[hl * 3 + 1];
+    const double rz = r2[6] * x + r2[7] * y + r2[8] * z + tj_s[hl * 3 + 2];
+    const float mx = static_cast<float>(wi * x + w2 * rx);
+    const float my = static_cast<float>(wi * y + w2 * ry);
+    const float mz = __fadd_rn(static_cast<float>(wi * z + w2 * rz), 0.05f);  // flame.py:164
+    const size_t o = (static_cast<size_t>(hg) * kV + v) * 3;
+    if (a.verts) { a.verts[o] = mx; a.verts[o + 1] = my; a.verts[o + 2] = mz; }
+    const float* R = R_s + hl * 9;
+    const float* st = st_s + hl * 8;
+    float out[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      float rv = __fmul_rn(R[i * 3], mx);
+      rv = __fmaf_rn(R[i * 3 + 1], my, rv);
+      rv = __fmaf_rn(R[i * 3 + 2], mz, rv);
+      out[i] = __fadd_rn(__fmul_rn(rv, st[0]), st[1 + i]);  // flame.py:198-199
+    }
+    out[0] = __fsub_rn(out[0], st[4]);  // detector.py:67-69
+    out[1] = __fsub_rn(out[1], st[5]);
+    a.proj[o] = __fdiv_rn(out[0], st[6]);
+    a.proj[o + 1] = __fdiv_rn(out[1], st[6]);
+    a.proj[o + 2] = __fdiv_rn(out[2], st[6]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- host
+struct FlameModel {
+  FlameDev dev;
+  void* blob = nullptr;
+};
+
+static size_t flame_smem_bytes(int heads, int lt_pad) {
+  return sizeof(double) * (2 * kLc * kTileV * 3 + static_cast<size_t>(lt_pad) * heads + heads * 3 + heads * 9) +
+         sizeof(float) * (heads * 9 + heads * 8);
+}
+
+int flame_model_create(const float* v_template, const float* shapedirs, const float* posedirs, const float* j_regressor,
+                       const float* lbs_weights, FlameModel** out, char* err, size_t errlen) {
+  // host re-layout in fp64 (exact widening of the fp32 constants the reference holds)
+  const size_t n_sdt = static_cast<size_t>(kL) * kVPad * 3, n_pd = static_cast<size_t>(kNPose) * kVPad * 3;
+  const size_t n_vt = static_cast<size_t>(kVPad) * 3, n_w = kVPad, n_js = 3 * kL;
+  const size_t total = n_sdt + n_pd + n_vt + 2 * n_w + n_js;
+  std::vector<double> host(total, 0.0);
+  double* sdt = host.data();
+  double* pd = sdt + n_sdt;
+  double* vt = pd + n_pd;
+  double* wI = vt + n_vt;
+  double* w2 = wI + n_w;
+  double* js2 = w2 + n_w;
+  for (int v = 0; v < kV; ++v)
+    for (int k = 0; k < 3; ++k) {
+      const float* src = shapedirs + (static_cast<size_t>(v) * 3 + k) * kL;
+      for (int l = 0; l < kL; ++l) sdt[(static_cast<size_t>(l) * kVPad + v) * 3 + k] = src[l];
+      vt[v * 3 + k] = v_template[v * 3 + k];
+      for (int m = 0; m < kNPose; ++m)  // posedirs is [36][15069]; jaw joint (index 2) -> rows 9..17
+        pd[(static_cast<size_t>(m) * kVPad + v) * 3 + k] = posedirs[static_cast<size_t>(9 + m) * (kV * 3) + v * 3 + k];
+    }
+  for (int v = 0; v < kV; ++v) {
+    const float* w = lbs_weights + v * 5;
+    wI[v] = static_cast<double>(w[0]) + w[1] + w[3] + w[4];
+    w2[v] = w[2];
+  }
+  FlameModel* m = new FlameModel();
+  for (int k = 0; k < 3; ++k) {
+    double jt = 0.0;
+    for (int v = 0; v < kV; ++v) jt += static_cast<double>(j_regressor[2 * kV + v]) * v_template[v * 3 + k];
+    m->dev.j2t[k] = jt;
+    for (int l = 0; l < kL; ++l) {
+      double s = 0.0;
+      for (int v = 0; v < kV; ++v) {
+        const float jr = j_regressor[2 * kV + v];
+        if (jr != 0.f) s += static_cast<double>(jr) * shapedirs[(static_cast<size_t>(v) * 3 + k) * kL + l];
+      }
+      js2[k * kL + l] = s;
+    }
+  }
+  cudaError_t e = cudaMalloc(&m->blob, total * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemcpy(m->blob, host.data(), total * sizeof(double), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    snprintf(err, errlen, "flame_model_create: %s", cudaGetErrorString(e));
+    if (m->blob) cudaFree(m->blob);
+    delete m;
+    return 1;
+  }
+  double* d = static_cast<double*>(m->blob);
+  m->dev.sdt = d; d += n_sdt;
+  m->dev.pd = d; d += n_pd;
+  m->dev.vt = d; d += n_vt;
+  m->dev.wI = d; d += n_w;
+  m->dev.w2 = d; d += n_w;
+  m->dev.js2 = d;
+  *out = m;
+  return 0;
+}
+
+void flame_model_destroy(FlameModel* m) {
+  if (!m) return;
+  if (m->blob) cudaFree(m->blob);
+  delete m;
+}
+
+template <int HG>
+static int launch_flame(const FlameArgs& a, cudaStream_t stream, char* err, size_t errlen) {
+  const int heads = kHPT * HG;
+  const int lt = a.ns + a.ne + kNPose;
+  const int lt_pad = (lt + kLc - 1) / kLc * kLc;
+  const size_t smem = flame_smem_bytes(heads, lt_pad);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(flame_decode_kernel<HG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      snprintf(err, errlen, "flame smem %zu: %s", smem, cudaGetErrorString(e));
+      return 2;
+    }
+    configured = smem;
+  }
+  dim3 grid(kVPad / kTileV, (a.n + heads - 1) / heads);
+  flame_decode_kernel<HG><<<grid, kTileV * HG, smem, stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(err, errlen, "flame launch: %s", cudaGetErrorString(e));
+    return 3;
+  }
+  return 0;
+}
+
+int flame_decode_launch(const FlameModel* m, const float* params, int n, const int* n_dev, int ns, int ne,
+                        const float* xform, float* verts, float* rot, float* proj, cudaStream_t stream, char* err,
+                        size_t errlen) {
+  if (n <= 0) return 0;
+  if (ns < 0 || ns > 300 || ne < 0 || ne > 100) {
+    snprintf(err, errlen, "flame_decode: live coefficient counts out of range (%d,%d)", ns, ne);
+    return 1;
+  }
+  FlameArgs a;
+  a.c = m->dev;
+  a.params = params; a.xform = xform; a.n_dev = n_dev; a.verts = verts; a.rot = rot; a.proj = proj;
+  a.n = n; a.ns = ns; a.ne = ne;
+  if (n > 16) return launch_flame<4>(a, stream, err, errlen);
+  return launch_flame<1>(a, stream, err, errlen);
+}
+
+}  // namespace vgh

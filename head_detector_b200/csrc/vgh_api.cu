@@ -1,0 +1,441 @@
+// C-ABI of libvggheads_b200.so (see include/vggheads_b200.h): plan executor for the conv network,
+// CUDA-graph capture of the whole device-side pipeline, and the stand-alone NMS / FLAME entry points.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/vggheads_b200.h"
+#include "aux_kernels.cuh"
+#include "conv_igemm.cuh"
+#include "flame_decode.cuh"
+#include "select_nms.cuh"
+
+using namespace vgh;
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_OK(expr)                                                                   \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) return fail(100, "%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+extern "C" int vgh_version(void) { return 1; }
+extern "C" const char* vgh_last_error(void) { return g_err; }
+
+// ------------------------------------------------------------------------------------------ FLAME
+struct vgh_flame {
+  FlameModel* model;
+};
+
+extern "C" int vgh_flame_create(const float* v_template, const float* shapedirs, const float* posedirs,
+                                const float* j_regressor, const float* lbs_weights, vgh_flame** out) {
+  if (!v_template || !shapedirs || !posedirs || !j_regressor || !lbs_weights || !out) return fail(1, "null argument");
+  FlameModel* m = nullptr;
+  int rc = flame_model_create(v_template, shapedirs, posedirs, j_regressor, lbs_weights, &m, g_err, sizeof(g_err));
+  if (rc) return rc;
+  *out = new vgh_flame{m};
+  return 0;
+}
+extern "C" void vgh_flame_destroy(vgh_flame* f) {
+  if (!f) return;
+  flame_model_destroy(f->model);
+  delete f;
+}
+extern "C" int vgh_flame_decode(const vgh_flame* f, const float* params_dev, int n, int n_shape_live, int n_expr_live,
+                                const float* xform_dev, float* verts_dev, float* rot_dev, float* proj_dev,
+                                void* stream) {
+  if (!f) return fail(1, "null flame handle");
+  if (n < 0) return fail(1, "negative head count");
+  if (n == 0) return 0;
+  if (!params_dev || !proj_dev) return fail(1, "null params/proj pointer");
+  return flame_decode_launch(f->model, params_dev, n, nullptr, n_shape_live, n_expr_live, xform_dev, verts_dev, rot_dev,
+                             proj_dev, static_cast<cudaStream_t>(stream), g_err, sizeof(g_err));
+}
+
+// ------------------------------------------------------------------------------------------ NMS
+extern "C" int vgh_select_nms(const float* boxes_dev, const float* scores_dev, int B, int A, float conf_thr,
+                              float iou_thr, int top_k, int keep_k, int32_t* keep_idx_dev, int32_t* keep_cnt_dev,
+                              float* keep_boxes_dev, float* keep_scores_dev, void* stream) {
+  if (!boxes_dev || !scores_dev || !keep_idx_dev || !keep_cnt_dev) return fail(1, "null argument");
+  if (B < 0 || A <= 0) return fail(1, "bad batch/anchor count");
+  return select_nms_launch(boxes_dev, scores_dev, B, A, conf_thr, iou_thr, top_k, keep_k, keep_idx_dev, keep_cnt_dev,
+                           keep_boxes_dev, keep_scores_dev, static_cast<cudaStream_t>(stream), g_err, sizeof(g_err));
+}
+
+// ------------------------------------------------------------------------------------------ detector
+struct OpRt {
+  vgh_op_desc d;
+  ConvLaunch L;
+  int bk;
+};
+
+struct vgh_detector {
+  int B = 0, S = 0, A = 0, keep_k = 100;
+  std::vector<vgh_buf_desc> bufs;
+  std::vector<void*> buf_ptr;
+  std::vector<size_t> buf_bytes;
+  std::vector<OpRt> ops;
+  __nv_bfloat16* weights = nullptr;
+  float* bias = nullptr;
+  float* stem_w = nullptr;
+  float* stem_b = nullptr;
+  DecodeLevels lv;
+  const vgh_flame* flame = nullptr;
+  uint8_t* input = nullptr;
+  float *boxes = nullptr, *scores = nullptr, *keep_boxes = nullptr, *keep_scores = nullptr;
+  int *keep_idx = nullptr, *keep_cnt = nullptr, *offsets = nullptr, *head_img = nullptr;
+  float *params = nullptr, *head_xform = nullptr, *verts = nullptr, *rot = nullptr, *img_xform = nullptr;
+  const float *ovr_boxes = nullptr, *ovr_scores = nullptr;
+  cudaGraphExec_t graph = nullptr;
+  float g_conf = -1.f, g_iou = -1.f;
+  int g_topk = -1;
+  int launches = 0;
+};
+
+static void pick_tile(int Ho, int Wo, int& tw, int& th) {
+  double best = -1.0;
+  tw = 1; th = 1;
+  for (int h = 1; h <= 128 && h <= Ho; ++h) {
+    int w = 128 / h;
+    if (w > Wo) w = Wo;
+    if (w < 1) continue;
+    const int tx = (Wo + w - 1) / w, ty = (Ho + h - 1) / h;
+    const double eff = static_cast<double>(Ho) * Wo / (static_cast<double>(tx) * ty * 128.0);
+    // prefer wide tiles on ties (longer contiguous runs per TMA box row)
+    if (eff > best + 1e-9 || (eff > best - 1e-9 && w > tw)) { best = eff; tw = w; th = h; }
+  }
+}
+
+static int auto_block_n(int cout, int up, int up_cout) {
+  const int lim = up ? up_cout : cout;
+  if (lim <= 256) return lim;
+  for (int n = 256; n >= 16; n -= 16)
+    if (lim % n == 0) return n;
+  return 16;
+}
+
+static int build_conv(vgh_detector* d, OpRt& o) {
+  const vgh_op_desc& q = o.d;
+  if (q.in_buf < 0 || q.in_buf >= (int)d->bufs.size() || q.out_buf < 0 || q.out_buf >= (int)d->bufs.size())
+    return fail(2, "op references unknown buffer");
+  const vgh_buf_desc& ib = d->bufs[q.in_buf];
+  const vgh_buf_desc& ob = d->bufs[q.out_buf];
+  ConvLaunch& L = o.L;
+  memset(&L, 0, sizeof(L));
+  if (q.cin % 32) return fail(2, "cin %d not a multiple of 32", q.cin);
+  o.bk = q.cin % 64 == 0 ? 64 : 32;
+  L.B = d->B;
+  L.stride = q.stride;
+  L.Ho = q.up ? ib.H : (ib.H + q.stride - 1) / q.stride;
+  L.Wo = q.up ? ib.W : (ib.W + q.stride - 1) / q.stride;
+  pick_tile(L.Ho, L.Wo, L.tw, L.th);
+  L.tiles_x = (L.Wo + L.tw - 1) / L.tw;
+  L.tiles_y = (L.Ho + L.th - 1) / L.th;
+  L.cin_off = q.in_coff;
+  L.cin = q.cin;
+  L.kw = q.ksize;
+  L.ntaps = q.ksize * q.ksize;
+  L.pad = q.ksize / 2;
+  L.n_total = q.cout;
+  L.block_n = q.block_n > 0 ? q.block_n : auto_block_n(q.cout, q.up, q.up_cout);
+  if (L.block_n % 16 || L.block_n > 256) return fail(2, "bad block_n %d", L.block_n);
+  if (q.n_pad % L.block_n) return fail(2, "n_pad %d not a multiple of block_n %d", q.n_pad, L.block_n);
+  if (q.k_total != L.ntaps * q.cin) return fail(2, "k_total mismatch");
+  L.out_cstride = ob.C;
+  L.out_coff = q.out_coff;
+  L.out_H = ob.H;
+  L.out_W = ob.W;
+  L.up = q.up;
+  L.up_cout = q.up_cout;
+  L.relu = q.relu;
+  L.out_fp32 = ob.fp32;
+  if (q.up) {
+    if (ob.H != 2 * ib.H || ob.W != 2 * ib.W) return fail(2, "transpose conv output buffer must be 2x the input");
+  } else if (ob.H != L.Ho || ob.W != L.Wo) {
+    return fail(2, "conv output buffer spatial mismatch (%dx%d vs %dx%d)", ob.H, ob.W, L.Ho, L.Wo);
+  }
+  L.bias = d->bias + q.b_off;
+  L.out = d->buf_ptr[q.out_buf];
+  if (q.res_buf >= 0) {
+    const vgh_buf_desc& rb = d->bufs[q.res_buf];
+    if (rb.H != L.Ho || rb.W != L.Wo || rb.fp32) return fail(2, "residual buffer mismatch");
+    L.res = static_cast<const __nv_bfloat16*>(d->buf_ptr[q.res_buf]);
+    L.res_cstride = rb.C;
+    L.res_coff = q.res_coff;
+    L.res_alpha = q.res_alpha;
+  }
+  L.stages = conv_pick_stages(L.block_n, o.bk);
+  int cols = 32;
+  while (cols < L.block_n) cols <<= 1;
+  L.tmem_cols = cols;
+  if (ib.fp32) return fail(2, "conv input must be bf16");
+  int rc = conv_make_tensor_maps(L, d->buf_ptr[q.in_buf], ib.C, ib.H, ib.W, d->weights + q.w_off, q.k_total, q.n_pad,
+                                 o.bk);
+  if (rc) return fail(3, "%s", conv_last_error());
+  return 0;
+}
+
+extern "C" void vgh_detector_destroy(vgh_detector* d) {
+  if (!d) return;
+  if (d->graph) cudaGraphExecDestroy(d->graph);
+  for (void* p : d->buf_ptr) cudaFree(p);
+  void* ptrs[] = {d->weights, d->bias, d->stem_w, d->stem_b, d->input, d->boxes, d->scores, d->keep_boxes,
+                  d->keep_scores, d->keep_idx, d->keep_cnt, d->offsets, d->head_img, d->params, d->head_xform,
+                  d->verts, d->rot, d->img_xform};
+  for (void* p : ptrs) cudaFree(p);
+  delete d;
+}
+
+template <typename T>
+static cudaError_t dmalloc(T** p, size_t count) {
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
+  if (e == cudaSuccess) e = cudaMemset(*p, 0, count * sizeof(T));
+  return e;
+}
+
+extern "C" int vgh_detector_create(const vgh_net_desc* n, const vgh_flame* flame, vgh_detector** out) {
+  if (!n || !out) return fail(1, "null argument");
+  if (n->batch < 1 || n->image_size < 64 || n->image_size % 32) return fail(1, "bad batch / image size");
+  int dev_count = 0;
+  if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) return fail(9, "no CUDA device (no CPU fallback)");
+  vgh_detector* d = new vgh_detector();
+  d->B = n->batch;
+  d->S = n->image_size;
+  d->keep_k = n->keep_k > 0 ? n->keep_k : 100;
+  d->flame = flame;
+  int rc = 0;
+  auto bail = [&](int code) { vgh_detector_destroy(d); return code; };
+
+  d->bufs.assign(n->bufs, n->bufs + n->n_bufs);
+  for (const vgh_buf_desc& b : d->bufs) {
+    const size_t bytes = static_cast<size_t>(d->B) * b.H * b.W * b.C * (b.fp32 ? 4 : 2);
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess || cudaMemset(p, 0, bytes) != cudaSuccess)
+      return bail(fail(4, "activation buffer allocation failed (%zu bytes)", bytes));
+    d->buf_ptr.push_back(p);
+    d->buf_bytes.push_back(bytes);
+  }
+  if (dmalloc(&d->weights, (size_t)n->n_weights) != cudaSuccess || dmalloc(&d->bias, (size_t)n->n_bias) != cudaSuccess ||
+      dmalloc(&d->stem_w, 48 * 27) != cudaSuccess || dmalloc(&d->stem_b, 48) != cudaSuccess)
+    return bail(fail(4, "weight allocation failed"));
+  cudaMemcpy(d->weights, n->weights_host, n->n_weights * 2, cudaMemcpyHostToDevice);
+  cudaMemcpy(d->bias, n->bias_host, n->n_bias * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(d->stem_w, n->stem_w_host, 48 * 27 * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(d->stem_b, n->stem_b_host, 48 * 4, cudaMemcpyHostToDevice);
+
+  for (int i = 0; i < n->n_ops; ++i) {
+    OpRt o;
+    o.d = n->ops[i];
+    o.bk = 0;
+    if (o.d.kind == VGH_OP_CONV) {
+      rc = build_conv(d, o);
+      if (rc) return bail(rc);
+    }
+    d->ops.push_back(o);
+  }
+  // decode bookkeeping
+  int a_off = 0;
+  for (int l = 0; l < 3; ++l) {
+    const vgh_buf_desc& rb = d->bufs[n->reg_buf[l]];
+    const vgh_buf_desc& fb = d->bufs[n->flame_buf[l]];
+    if (!rb.fp32 || !fb.fp32 || rb.H != fb.H) return bail(fail(2, "raw head buffers must be fp32"));
+    d->lv.reg[l] = static_cast<const float*>(d->buf_ptr[n->reg_buf[l]]);
+    d->lv.flame[l] = static_cast<const float*>(d->buf_ptr[n->flame_buf[l]]);
+    d->lv.a_off[l] = a_off;
+    d->lv.W[l] = rb.W;
+    d->lv.hw[l] = rb.H * rb.W;
+    d->lv.stride[l] = static_cast<float>(d->S / rb.H);
+    d->lv.reg_cstride = rb.C;
+    d->lv.flame_cstride = fb.C;
+    a_off += rb.H * rb.W;
+  }
+  d->lv.a_off[3] = a_off;
+  d->A = a_off;
+  const size_t B = d->B, A = d->A, K = d->keep_k, cap = B * K;
+  if (dmalloc(&d->input, B * d->S * d->S * 3) != cudaSuccess || dmalloc(&d->boxes, B * A * 4) != cudaSuccess ||
+      dmalloc(&d->scores, B * A) != cudaSuccess || dmalloc(&d->keep_boxes, cap * 4) != cudaSuccess ||
+      dmalloc(&d->keep_scores, cap) != cudaSuccess || dmalloc(&d->keep_idx, cap) != cudaSuccess ||
+      dmalloc(&d->keep_cnt, B) != cudaSuccess || dmalloc(&d->offsets, B + 1) != cudaSuccess ||
+      dmalloc(&d->head_img, cap) != cudaSuccess || dmalloc(&d->params, cap * VGH_NUM_PARAMS) != cudaSuccess ||
+      dmalloc(&d->head_xform, cap * 3) != cudaSuccess || dmalloc(&d->verts, cap * VGH_NUM_VERTS * 3) != cudaSuccess ||
+      dmalloc(&d->rot, cap * 9) != cudaSuccess || dmalloc(&d->img_xform, B * 3) != cudaSuccess)
+    return bail(fail(4, "result buffer allocation failed"));
+  {
+    std::vector<float> xf(B * 3, 0.f);
+    for (size_t i = 0; i < B; ++i) xf[i * 3 + 2] = 1.f;
+    cudaMemcpy(d->img_xform, xf.data(), xf.size() * 4, cudaMemcpyHostToDevice);
+  }
+  CUDA_OK(cudaDeviceSynchronize());
+  *out = d;
+  return 0;
+}
+
+static int run_forward(vgh_detector* d, const uint8_t* images, cudaStream_t s, int* launches) {
+  for (OpRt& o : d->ops) {
+    int rc = 0;
+    switch (o.d.kind) {
+      case VGH_OP_STEM:
+        rc = stem_conv_launch(images, d->stem_w, d->stem_b, static_cast<__nv_bfloat16*>(d->buf_ptr[o.d.out_buf]), d->B,
+                              d->S, s);
+        if (rc) return fail(5, "stem launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        break;
+      case VGH_OP_CONV:
+        rc = conv_launch(o.L, o.bk, s);
+        if (rc) return fail(5, "%s", conv_last_error());
+        break;
+      case VGH_OP_SPP: {
+        const vgh_buf_desc& b = d->bufs[o.d.in_buf];
+        rc = spp_pool_launch(static_cast<__nv_bfloat16*>(d->buf_ptr[o.d.in_buf]), d->B, b.H, b.W, o.d.cin, s);
+        if (rc) return fail(5, "spp launch failed");
+        break;
+      }
+      default:
+        return fail(5, "unknown op kind %d", o.d.kind);
+    }
+    if (launches) ++*launches;
+  }
+  if (box_decode_launch(d->lv, d->boxes, d->scores, d->B, d->A, s)) return fail(5, "box decode launch failed");
+  if (launches) ++*launches;
+  if (d->ovr_boxes && d->ovr_scores) {
+    CUDA_OK(cudaMemcpyAsync(d->boxes, d->ovr_boxes, sizeof(float) * 4 * d->B * d->A, cudaMemcpyDeviceToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(d->scores, d->ovr_scores, sizeof(float) * d->B * d->A, cudaMemcpyDeviceToDevice, s));
+  }
+  return 0;
+}
+
+static int run_post(vgh_detector* d, float conf, float iou, int top_k, const float* xform, cudaStream_t s, int* launches) {
+  int rc = select_nms_launch(d->boxes, d->scores, d->B, d->A, conf, iou, top_k, d->keep_k, d->keep_idx, d->keep_cnt,
+                             d->keep_boxes, d->keep_scores, s, g_err, sizeof(g_err));
+  if (rc) return rc;
+  if (flame_gather_launch(d->lv, d->keep_idx, d->keep_cnt, d->B, d->keep_k, xform, d->offsets, d->offsets + d->B,
+                          d->params, d->head_xform, d->head_img, s))
+    return fail(5, "gather launch failed");
+  if (launches) *launches += 3;
+  if (d->flame) {
+    rc = flame_decode_launch(d->flame->model, d->params, d->B * d->keep_k, d->offsets + d->B, 128, 64, d->head_xform,
+                             nullptr, d->rot, d->verts, s, g_err, sizeof(g_err));
+    if (rc) return rc;
+    if (launches) ++*launches;
+  }
+  return 0;
+}
+
+extern "C" int vgh_detector_forward(vgh_detector* d, const uint8_t* images_dev, void* stream) {
+  if (!d || !images_dev) return fail(1, "null argument");
+  return run_forward(d, images_dev, static_cast<cudaStream_t>(stream), nullptr);
+}
+extern "C" int vgh_detector_postprocess(vgh_detector* d, float conf_thr, float iou_thr, int top_k,
+                                        const float* img_xform_dev, void* stream) {
+  if (!d) return fail(1, "null argument");
+  return run_post(d, conf_thr, iou_thr, top_k, img_xform_dev ? img_xform_dev : d->img_xform,
+                  static_cast<cudaStream_t>(stream), nullptr);
+}
+extern "C" int vgh_detector_dense_flame(vgh_detector* d, float* flame_dev, void* stream) {
+  if (!d || !flame_dev) return fail(1, "null argument");
+  return flame_dense_launch(d->lv, flame_dev, d->B, d->A, static_cast<cudaStream_t>(stream)) ? fail(5, "dense flame launch failed") : 0;
+}
+extern "C" void* vgh_detector_output(vgh_detector* d, int which) {
+  if (!d) return nullptr;
+  switch (which) {
+    case VGH_OUT_BOXES: return d->boxes;
+    case VGH_OUT_SCORES: return d->scores;
+    case VGH_OUT_KEEP_IDX: return d->keep_idx;
+    case VGH_OUT_KEEP_CNT: return d->keep_cnt;
+    case VGH_OUT_KEEP_BOXES: return d->keep_boxes;
+    case VGH_OUT_KEEP_SCORES: return d->keep_scores;
+    case VGH_OUT_HEAD_OFFSETS: return d->offsets;
+    case VGH_OUT_HEAD_PARAMS: return d->params;
+    case VGH_OUT_HEAD_VERTS: return d->verts;
+    case VGH_OUT_HEAD_ROT: return d->rot;
+    case VGH_OUT_INPUT: return d->input;
+  }
+  return nullptr;
+}
+extern "C" int vgh_detector_num_anchors(const vgh_detector* d) { return d ? d->A : 0; }
+extern "C" int vgh_detector_launch_count(const vgh_detector* d) { return d ? d->launches : 0; }
+extern "C" int vgh_detector_read_buffer(vgh_detector* d, int buf, void* host_dst, size_t bytes) {
+  if (!d || buf < 0 || buf >= (int)d->buf_ptr.size() || !host_dst) return fail(1, "bad buffer id");
+  if (bytes > d->buf_bytes[buf]) return fail(1, "read of %zu bytes exceeds buffer (%zu)", bytes, d->buf_bytes[buf]);
+  CUDA_OK(cudaMemcpy(host_dst, d->buf_ptr[buf], bytes, cudaMemcpyDeviceToHost));
+  return 0;
+}
+// Synthetic-workload hook (bench / tests): after box decode, overwrite boxes/scores with caller data
+// (random weights never produce detections).  Pass NULLs to disable.
+extern "C" int vgh_detector_set_override(vgh_detector* d, const float* boxes_dev, const float* scores_dev) {
+  if (!d) return fail(1, "null argument");
+  d->ovr_boxes = boxes_dev;
+  d->ovr_scores = scores_dev;
+  if (d->graph) { cudaGraphExecDestroy(d->graph); d->graph = nullptr; }
+  return 0;
+}
+
+static int ensure_graph(vgh_detector* d, float conf, float iou, int top_k, cudaStream_t s) {
+  if (d->graph && d->g_conf == conf && d->g_iou == iou && d->g_topk == top_k) return 0;
+  if (d->graph) { cudaGraphExecDestroy(d->graph); d->graph = nullptr; }
+  // one eager pass first: sets the max-dynamic-smem attributes outside of capture and surfaces errors
+  int launches = 0;
+  int rc = run_forward(d, d->input, s, &launches);
+  if (!rc) rc = run_post(d, conf, iou, top_k, d->img_xform, s, &launches);
+  if (rc) return rc;
+  CUDA_OK(cudaStreamSynchronize(s));
+  d->launches = launches;
+  cudaGraph_t g = nullptr;
+  CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  rc = run_forward(d, d->input, s, nullptr);
+  if (!rc) rc = run_post(d, conf, iou, top_k, d->img_xform, s, nullptr);
+  cudaError_t e = cudaStreamEndCapture(s, &g);
+  if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+  if (e != cudaSuccess) return fail(6, "graph capture failed: %s", cudaGetErrorString(e));
+  e = cudaGraphInstantiate(&d->graph, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) return fail(6, "graph instantiate failed: %s", cudaGetErrorString(e));
+  d->g_conf = conf; d->g_iou = iou; d->g_topk = top_k;
+  return 0;
+}
+
+extern "C" int vgh_detector_run_device(vgh_detector* d, float conf_thr, float iou_thr, int top_k, void* stream) {
+  if (!d) return fail(1, "null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int rc = ensure_graph(d, conf_thr, iou_thr, top_k, s);
+  if (rc) return rc;
+  CUDA_OK(cudaGraphLaunch(d->graph, s));
+  return 0;
+}
+
+extern "C" int vgh_detector_run_host(vgh_detector* d, const uint8_t* images_host, const float* img_xform_host,
+                                     float conf_thr, float iou_thr, int top_k, int32_t* keep_cnt_host,
+                                     float* keep_boxes_host, float* keep_scores_host, float* params_host,
+                                     float* verts_host, int max_heads, int32_t* total_heads, void* stream) {
+  if (!d || !images_host || !keep_cnt_host || !total_heads) return fail(1, "null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int rc = ensure_graph(d, conf_thr, iou_thr, top_k, s);
+  if (rc) return rc;
+  const size_t B = d->B, K = d->keep_k;
+  CUDA_OK(cudaMemcpyAsync(d->input, images_host, B * d->S * d->S * 3, cudaMemcpyHostToDevice, s));
+  if (img_xform_host) CUDA_OK(cudaMemcpyAsync(d->img_xform, img_xform_host, B * 3 * 4, cudaMemcpyHostToDevice, s));
+  CUDA_OK(cudaGraphLaunch(d->graph, s));
+  CUDA_OK(cudaMemcpyAsync(keep_cnt_host, d->keep_cnt, B * 4, cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaMemcpyAsync(total_heads, d->offsets + B, 4, cudaMemcpyDeviceToHost, s));
+  if (keep_boxes_host) CUDA_OK(cudaMemcpyAsync(keep_boxes_host, d->keep_boxes, B * K * 16, cudaMemcpyDeviceToHost, s));
+  if (keep_scores_host) CUDA_OK(cudaMemcpyAsync(keep_scores_host, d->keep_scores, B * K * 4, cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  int n = *total_heads;
+  if (n > max_heads) n = max_heads;
+  if (n > 0) {
+    if (params_host) CUDA_OK(cudaMemcpyAsync(params_host, d->params, (size_t)n * VGH_NUM_PARAMS * 4, cudaMemcpyDeviceToHost, s));
+    if (verts_host) CUDA_OK(cudaMemcpyAsync(verts_host, d->verts, (size_t)n * VGH_NUM_VERTS * 12, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+  }
+  return 0;
+}

@@ -1,0 +1,160 @@
+/* vggheads_b200 - C ABI of the B200-native VGGHeads inference hot path.
+ *
+ * The reference (KupynOrest/head_detector) has no FFI layer; its seam is three Python callables
+ * (SURVEY.md 8b).  Each entry point below names the reference interface it replaces so a
+ * maintainer can bind it from head_detector/detector.py (see INTEGRATION.md for the ctypes stub):
+ *
+ *   vgh_detector_forward      <- `self.model(image)`            head_detector/detector.py:58-59
+ *                                (TorchScript YoloHeads_L: yolo_head_training/yolo_head/
+ *                                 yolo_head_ndfl_heads.py:117-175, yolo_head_dfl_head.py:141-186)
+ *   vgh_select_nms            <- `utils.nms(...)`               head_detector/utils.py:159-194
+ *                                (batched twin: yolo_heads_post_prediction_callback.py:55-97)
+ *   vgh_flame_decode          <- `reproject_spatial_vertices`   head_detector/flame.py:179-208
+ *                                + FLAMELayer.forward            head_detector/flame.py:122-169
+ *                                + vertex un-letterboxing        head_detector/detector.py:66-69
+ *   vgh_detector_postprocess  <- `HeadDetector._postprocess`    head_detector/detector.py:92-95
+ *   vgh_detector_run_host     <- `HeadDetector.__call__` minus host glue, batched; HOST buffers
+ *
+ * Conventions: plain C, no exceptions across the boundary; every function returns 0 on success or a
+ * non-zero status, and vgh_last_error() returns a thread-local message.  "dev" pointers are CUDA
+ * device pointers owned by the caller unless stated; streams are cudaStream_t passed as void*.
+ * Handles are immutable after creation except for their internal work buffers: use one handle per
+ * stream.  There is NO CPU fallback: every entry point needs a CUDA device (sm_100a).
+ */
+#ifndef VGGHEADS_B200_H
+#define VGGHEADS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VGH_NUM_VERTS 5023
+#define VGH_NUM_PARAMS 413 /* [shape300|expr100|jaw3|rot6d6|transl3|scale1], head_info.py:12-21,54-78 */
+
+typedef struct vgh_flame vgh_flame;
+typedef struct vgh_detector vgh_detector;
+
+int vgh_version(void);
+const char* vgh_last_error(void);
+
+/* ---------------------------------------------------------------------------------- FLAME decode */
+/* Constants exactly as FLAMELayer registers them (flame.py:43-95), fp32 HOST arrays:
+ * v_template[5023*3], shapedirs[5023*3*400], posedirs[36*15069], j_regressor[5*5023],
+ * lbs_weights[5023*5].  Uploaded (re-laid-out) once. */
+int vgh_flame_create(const float* v_template, const float* shapedirs, const float* posedirs, const float* j_regressor,
+                     const float* lbs_weights, vgh_flame** out);
+void vgh_flame_destroy(vgh_flame* f);
+/* params_dev [n,413]; n_shape_live / n_expr_live: leading shape / expression coefficients that may
+ * be non-zero (300/100 = general; 128/64 for rows emitted by the network).  xform_dev: optional
+ * [n,3] = (pad_x, pad_y, letterbox_scale) applied as detector.py:67-69 (NULL = (0,0,1)).
+ * Outputs (device, fp32): verts_dev [n,5023,3] model-space vertices incl. +0.05 z (may be NULL),
+ * rot_dev [n,9] row-major rotation (may be NULL), proj_dev [n,5023,3] = ((R v) * max(s,1e-8) + t
+ * - pad) / scale.  n == 0 is a no-op (flame.py:186-189). */
+int vgh_flame_decode(const vgh_flame* f, const float* params_dev, int n, int n_shape_live, int n_expr_live,
+                     const float* xform_dev, float* verts_dev, float* rot_dev, float* proj_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------- select + NMS */
+/* boxes_dev [B,A,4] xyxy, scores_dev [B,A] (>= 0).  Per image: score >= conf_thr, best top_k
+ * (<= 1024) by score, greedy NMS (suppress iff IoU > iou_thr), first keep_k survivors in
+ * descending-score order.  keep_idx_dev [B,keep_k] int32 ORIGINAL anchor ids (-1 padded),
+ * keep_cnt_dev [B] int32; keep_boxes_dev [B,keep_k,4] / keep_scores_dev [B,keep_k] optional. */
+int vgh_select_nms(const float* boxes_dev, const float* scores_dev, int B, int A, float conf_thr, float iou_thr,
+                   int top_k, int keep_k, int32_t* keep_idx_dev, int32_t* keep_cnt_dev, float* keep_boxes_dev,
+                   float* keep_scores_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------- conv network */
+/* Execution plan of the deploy-form network, produced by head_detector_b200/arch.py from the
+ * reference's arch yaml (yolo_heads_l_arch_params.yaml).  Activations are NHWC bf16 buffers;
+ * every op reads/writes a channel slice so that no concat is ever materialised. */
+typedef struct {
+  int32_t H, W, C;   /* spatial size and channels per pixel */
+  int32_t fp32;      /* 0 = bf16, 1 = fp32 (raw head outputs) */
+} vgh_buf_desc;
+
+enum { VGH_OP_STEM = 0, VGH_OP_CONV = 1, VGH_OP_SPP = 2 };
+
+typedef struct {
+  int32_t kind;
+  int32_t in_buf, in_coff, cin;      /* cin: channels per tap (multiple of 32) */
+  int32_t out_buf, out_coff, cout;   /* cout: stored channels (multiple of 16) */
+  int32_t ksize, stride;             /* 1 or 3; stride 1 or 2 */
+  int32_t relu, up;                  /* up=1: 2x2 stride-2 transpose conv, cout = 4*up_cout */
+  int32_t up_cout;
+  int32_t res_buf, res_coff;         /* residual source (res_buf < 0: none) */
+  float res_alpha;
+  int32_t n_pad, k_total, block_n;   /* packed weight matrix [n_pad][k_total] bf16, UMMA N */
+  int64_t w_off, b_off;              /* element offsets into the weight / bias blobs */
+} vgh_op_desc;
+
+typedef struct {
+  int32_t batch, image_size;
+  int32_t n_bufs, n_ops;
+  const vgh_buf_desc* bufs;
+  const vgh_op_desc* ops;
+  const uint16_t* weights_host;  /* bf16 bits, all packed conv weights */
+  int64_t n_weights;
+  const float* bias_host;
+  int64_t n_bias;
+  const float* stem_w_host;      /* [48][27] fp32 (ky,kx,c), already divided by 255 */
+  const float* stem_b_host;      /* [48] */
+  int32_t reg_buf[3], flame_buf[3]; /* raw head output buffers per level (fp32) */
+  int32_t keep_k;                /* capacity of survivors per image (keep_top_k, utils.py:166) */
+} vgh_net_desc;
+
+int vgh_detector_create(const vgh_net_desc* net, const vgh_flame* flame, vgh_detector** out);
+void vgh_detector_destroy(vgh_detector* d);
+
+/* images_dev: uint8 [B,S,S,3] RGB (letterboxed; the /255 of detector.py:51 is folded into the stem).
+ * Fills the internal boxes [B,A,4] / scores [B,A] / raw-flame buffers. */
+int vgh_detector_forward(vgh_detector* d, const uint8_t* images_dev, void* stream);
+/* select+NMS, survivor FLAME rows, FLAME decode.  img_xform_dev optional [B,3] (pad_x,pad_y,scale). */
+int vgh_detector_postprocess(vgh_detector* d, float conf_thr, float iou_thr, int top_k, const float* img_xform_dev,
+                             void* stream);
+/* The model-output boundary of the reference (boxes, scores, flame[B,A,413]) for parity tests:
+ * expands the compact raw rows to the dense 413-wide tensor into flame_dev [B,A,413]. */
+int vgh_detector_dense_flame(vgh_detector* d, float* flame_dev, void* stream);
+
+/* Device views of the internal result buffers (valid until destroy). */
+enum {
+  VGH_OUT_BOXES = 0,       /* float [B,A,4] */
+  VGH_OUT_SCORES = 1,      /* float [B,A] */
+  VGH_OUT_KEEP_IDX = 2,    /* int32 [B,keep_k] */
+  VGH_OUT_KEEP_CNT = 3,    /* int32 [B] */
+  VGH_OUT_KEEP_BOXES = 4,  /* float [B,keep_k,4] */
+  VGH_OUT_KEEP_SCORES = 5, /* float [B,keep_k] */
+  VGH_OUT_HEAD_OFFSETS = 6,/* int32 [B+1] exclusive prefix of keep_cnt; [B] = total heads */
+  VGH_OUT_HEAD_PARAMS = 7, /* float [total,413] packed image-major */
+  VGH_OUT_HEAD_VERTS = 8,  /* float [total,5023,3] */
+  VGH_OUT_HEAD_ROT = 9,    /* float [total,9] */
+  VGH_OUT_INPUT = 10       /* uint8 [B,S,S,3] internal staging image buffer */
+};
+void* vgh_detector_output(vgh_detector* d, int which);
+int vgh_detector_num_anchors(const vgh_detector* d);
+/* Copy an activation buffer to the host (debug / layer-wise parity). */
+int vgh_detector_read_buffer(vgh_detector* d, int buf, void* host_dst, size_t bytes);
+
+/* End to end with HOST buffers (pinned recommended): H2D of images, forward, postprocess, D2H of
+ * counts / kept boxes / kept scores / packed params and vertices.  The whole device side replays
+ * one CUDA graph.  verts_host capacity = max_heads*5023*3 floats; returns total heads in
+ * *total_heads (heads beyond max_heads are not copied). */
+int vgh_detector_run_host(vgh_detector* d, const uint8_t* images_host, const float* img_xform_host, float conf_thr,
+                          float iou_thr, int top_k, int32_t* keep_cnt_host, float* keep_boxes_host,
+                          float* keep_scores_host, float* params_host, float* verts_host, int max_heads,
+                          int32_t* total_heads, void* stream);
+/* Same device work (graph replay) with inputs already resident in the internal staging buffer and
+ * results left on the device - the kernel-only timing path. */
+int vgh_detector_run_device(vgh_detector* d, float conf_thr, float iou_thr, int top_k, void* stream);
+/* Synthetic-workload hook (bench/tests): after box decode, overwrite the internal boxes [B,A,4] and
+ * scores [B,A] with caller data (random weights never yield detections).
+ * The copy is part of the timed device work.  NULL, NULL disables it. */
+int vgh_detector_set_override(vgh_detector* d, const float* boxes_dev, const float* scores_dev);
+/* Number of kernel launches one forward+postprocess issues (graph nodes), for reporting. */
+int vgh_detector_launch_count(const vgh_detector* d);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VGGHEADS_B200_H */

@@ -1,0 +1,128 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference python.  TEST INFRASTRUCTURE ONLY.
+
+Runs only in the build container (needs /root/reference).  The reference package is imported
+from where it lies with three stand-ins on sys.path (oracle/shims): `chumpy` (unpickle stub),
+`smplx` (its `lbs` is routed to oracle.flame_oracle.lbs_torch - smplx==0.1.26 is not
+installed here) and `Sim3DR_Cython` (import stub, rasteriser is off the hot path).
+
+    python oracle/make_golden.py
+
+Fixtures written (all small, committed):
+  flame_1json.npz        the reference's own known-answer vector yolo_head_training/tests/1.json
+  flame_ref_heads.npz    reference `reproject_spatial_vertices` (flame.py:179-208) on seeded heads
+  nms_ref_cases.npz      reference `utils.nms` (utils.py:159-194) on seeded anchors, with the
+                         surviving ORIGINAL anchor ids recovered through an index column
+  parse_ref.npz          reference `HeadDetector._parse_predictions` (detector.py:61-90)
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = "/root/reference"
+sys.path[:0] = [os.path.join(HERE, "shims"), REF, ROOT]
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def network_like_heads(n: int, seed: int, size: float = 640.0) -> torch.Tensor:
+    """413-float rows shaped like what the network emits."""
+    g = torch.Generator().manual_seed(seed)
+    p = torch.zeros(n, 413)
+    p[:, 0:128] = 3 * torch.tanh(torch.randn(n, 128, generator=g))
+    p[:, 300:364] = 3 * torch.tanh(torch.randn(n, 64, generator=g))
+    p[:, 400:403] = 0.1 * torch.randn(n, 3, generator=g)
+    p[:, 403:409] = torch.randn(n, 6, generator=g)
+    p[:, 409:411] = torch.rand(n, 2, generator=g) * size
+    p[:, 411] = 10 * torch.randn(n, generator=g)
+    p[:, 412] = 200 + 400 * torch.rand(n, generator=g)
+    return p
+
+
+def clustered_anchors(n_anchor: int, n_clusters: int, per_cluster: int, seed: int, size: float = 640.0, bg_hi: float = 0.3):
+    """Seeded boxes/scores with engineered clusters (tie-free scores)."""
+    g = torch.Generator().manual_seed(seed)
+    boxes = torch.rand(n_anchor, 4, generator=g) * size
+    boxes = torch.stack(
+        [torch.minimum(boxes[:, 0], boxes[:, 2]), torch.minimum(boxes[:, 1], boxes[:, 3]),
+         torch.maximum(boxes[:, 0], boxes[:, 2]) + 1, torch.maximum(boxes[:, 1], boxes[:, 3]) + 1], dim=1)
+    scores = torch.rand(n_anchor, generator=g) * bg_hi
+    perm = torch.randperm(n_anchor, generator=g)
+    k = 0
+    for c in range(n_clusters):
+        cx, cy = (torch.rand(2, generator=g) * (size - 200) + 100).tolist()
+        half = float(torch.rand(1, generator=g) * 50 + 40)
+        for _ in range(per_cluster):
+            i = int(perm[k]); k += 1
+            j = (torch.rand(4, generator=g) - 0.5) * 12
+            boxes[i] = torch.tensor([cx - half, cy - half, cx + half, cy + half]) + j
+            scores[i] = 0.55 + 0.4 * float(torch.rand(1, generator=g))
+    scores = scores + torch.arange(n_anchor) * 1e-7  # no exact ties
+    return boxes.float(), scores.float()
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    from head_detector.flame import FLAMELayer, reproject_spatial_vertices  # the reference, unmodified
+    from head_detector.head_info import FlameParams
+    from head_detector.utils import nms as ref_nms, calculate_rpy
+    from head_detector.detector import HeadDetector
+
+    # --- 1. the reference's own fixture -------------------------------------------------------
+    rec = json.load(open(os.path.join(REF, "yolo_head_training", "tests", "1.json")))[0]
+    np.savez_compressed(
+        os.path.join(OUT, "flame_1json.npz"),
+        params=np.asarray(rec["3dmm_params"], dtype=np.float64),
+        vertices_3d=np.asarray(rec["3d_vertices"], dtype=np.float64),
+        projected_vertices=np.asarray(rec["projected_vertices"], dtype=np.float64),
+    )
+    flame = FLAMELayer()
+    p1 = torch.tensor(rec["3dmm_params"], dtype=torch.float32)[None]
+    v1 = flame.forward(FlameParams.from_3dmm(p1), zero_rot=False)[0].numpy()
+    print("reference FLAMELayer vs 1.json: max abs", np.abs(v1 - np.asarray(rec["3d_vertices"])).max())
+
+    # --- 2. reference reproject on seeded heads -----------------------------------------------
+    heads = torch.cat([network_like_heads(5, seed=11), p1 * 1.0])  # 5 network-like + the dense 400-coef fixture row
+    heads[5, 409:412] = torch.tensor([311.5, 207.25, 3.0]); heads[5, 412] = 350.0
+    verts, rot, proj = reproject_spatial_vertices(flame, heads, to_2d=False)
+    np.savez_compressed(os.path.join(OUT, "flame_ref_heads.npz"), params=heads.numpy(), vertices=verts.numpy(),
+                        rotation=rot.numpy(), projected=proj.numpy())
+
+    # --- 3. reference nms, anchor ids recovered through column 0 of the flame tensor -----------
+    cases = {}
+    for name, (na, ncl, per, seed, bg) in {
+        "few": (8400, 8, 12, 3, 0.3),          # ~96 candidates
+        "many": (8400, 40, 12, 4, 0.9),        # >1000 candidates -> top-k path
+        "none": (8400, 0, 0, 5, 0.3),          # nothing above threshold
+        "hires": (33600, 30, 14, 6, 0.6),      # S=1280 anchor count
+    }.items():
+        boxes, scores = clustered_anchors(na, ncl, per, seed, size=640.0 if na == 8400 else 1280.0, bg_hi=bg)
+        tag = torch.zeros(na, 413); tag[:, 0] = torch.arange(na)
+        b, s, f = ref_nms(boxes[None], scores[None, :, None], tag[None], confidence_threshold=0.5)
+        cases[f"{name}_boxes"] = boxes.numpy(); cases[f"{name}_scores"] = scores.numpy()
+        cases[f"{name}_keep"] = f[:, 0].long().numpy(); cases[f"{name}_keep_scores"] = s.numpy()
+        print(name, "candidates", int((scores >= 0.5).sum()), "kept", len(s))
+    np.savez_compressed(os.path.join(OUT, "nms_ref_cases.npz"), **cases)
+
+    # --- 4. reference _parse_predictions (letterboxed: pad (0,80), scale 0.5) -------------------
+    det = object.__new__(HeadDetector)
+    det._image_size, det._device, det._flame = 640, torch.device("cpu"), flame
+    hp = network_like_heads(3, seed=21)
+    hb = torch.tensor([[10.4, 90.6, 200.5, 300.5], [-5.0, 100.0, 650.0, 500.49], [300.5, 301.5, 420.5, 480.5]])
+    hs = torch.tensor([0.9, 0.8, 0.7])
+    res = det._parse_predictions(hb.clone(), hs.clone(), hp.clone(), {"padding": (0, 80), "scale": 0.5})
+    np.savez_compressed(
+        os.path.join(OUT, "parse_ref.npz"), params=hp.numpy(), boxes=hb.numpy(), scores=hs.numpy(),
+        bbox_xywh=np.array([[int(v) for v in h.bbox] for h in res]),
+        vertices_3d=np.stack([h.vertices_3d for h in res]),
+        rpy=np.array([[h.head_pose.roll, h.head_pose.pitch, h.head_pose.yaw] for h in res], dtype=np.float64),
+        out_scale=np.array([float(h.flame_params.scale) for h in res]),
+    )
+    print("golden fixtures written to", OUT)
+
+
+if __name__ == "__main__":
+    main()
