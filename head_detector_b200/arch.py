@@ -1,0 +1,313 @@
+"""YoloHeads_L (VGGHeads_L) as an execution plan for libvggheads_b200.
+
+Architecture source: the reference's arch spec
+`yolo_head_training/configs/arch_params/yolo_heads_l_arch_params.yaml:1-141` (widths, depths),
+`yolo_head_training/yolo_head/yolo_head_dfl_head.py:23-135` (per-level head) and the YoloNAS
+building blocks of super_gradients (stem / stage / CSP / SPP / up- / down-stage; SURVEY.md
+Appendix A.1).  Everything is in DEPLOY form: each QARepVGG block or Conv-BN-ReLU is one conv +
+bias + ReLU (Appendix A.2); `fold_*` helpers below produce that form from as-trained tensors.
+
+What this module adds on top of the spec is the B200 data layout:
+  * activations are NHWC bf16 buffers; every conv writes straight into a channel slice of its
+    consumer's buffer, so no torch.cat of the reference graph is ever materialised;
+  * convs that read the same tensor are fused along N (CSP conv1||conv2, head stems, first tower
+    layers), tiny parallel convs are fused as block-diagonal GEMMs (pred convs, 32-wide towers);
+  * the CSP concat is stored as [a | b | b1..bn] and conv3's K columns are permuted at pack time;
+  * weights are packed K-major [Cout_pad][tap][Cin] bf16 for 2-D TMA boxes.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+STEM_OUT = 48
+BACKBONE = [(96, 2, 96), (192, 3, 128), (384, 5, 256), (768, 2, 512)]  # (out, blocks, hidden) yaml:12-38
+NECKS = {"neck1": (192, 4, 128), "neck2": (96, 4, 128), "neck3": (192, 4, 128), "neck4": (384, 4, 256)}  # yaml:52-88
+HEADS = [(96, 128, 8), (192, 256, 16), (384, 512, 32)]  # (in, bbox_inter, stride) yaml:96-138
+FLAME_INTER = 256
+TOWERS = [("shape", 256, 128), ("expr", 128, 64), ("rot", 32, 6), ("jaw", 32, 3), ("scale", 32, 1), ("transl", 32, 3)]
+REG_ROWS, FLAME_ROWS = 80, 208  # 68+1 (+pad) ; 128+64+6+3+3+1 (+pad)
+# raw flame row layout: [shape128 | expr64 | rot6 | jaw3 | transl3 | scale1 | pad3]
+RAW_ROW_OFF = {"shape": 0, "expr": 128, "rot": 192, "jaw": 198, "transl": 201, "scale": 204}
+
+
+@dataclass
+class Part:
+    """One reference conv inside a (possibly fused) GEMM: rows [row, row+cout) of the packed matrix,
+    reading logical input channels [log, log+n) from physical columns [phys, phys+n) per segment."""
+    name: str
+    row: int
+    cout: int
+    segs: List[Tuple[int, int, int]]  # (phys_col, logical_cin, n)
+    transposed: bool = False
+
+
+@dataclass
+class Op:
+    kind: int
+    src: Tuple[int, int, int] = (0, 0, 0)   # (buf, coff, cin)
+    dst: Tuple[int, int] = (0, 0)           # (buf, coff)
+    cout: int = 0                           # stored channels
+    k: int = 1
+    stride: int = 1
+    relu: int = 1
+    up: int = 0
+    up_cout: int = 0
+    res: Optional[Tuple[int, int, str]] = None  # (buf, coff, alpha weight name)
+    parts: List[Part] = field(default_factory=list)
+    n_pad: int = 0
+    label: str = ""
+
+
+class Plan:
+    def __init__(self, image_size: int):
+        assert image_size % 32 == 0
+        self.S = image_size
+        self.bufs: List[Tuple[int, int, int, int]] = []
+        self.buf_names: Dict[str, int] = {}
+        self.ops: List[Op] = []
+        self.reg_buf: List[int] = []
+        self.flame_buf: List[int] = []
+
+    # -- helpers
+    def buf(self, name, res, C, fp32=0):
+        self.bufs.append((res, res, C, fp32))
+        self.buf_names[name] = len(self.bufs) - 1
+        return len(self.bufs) - 1
+
+    def conv(self, label, src, dst, parts, k=1, stride=1, relu=1, res=None, up=0, up_cout=0, cout=None):
+        rows = max(p.row + p.cout for p in parts) if not up else 4 * up_cout
+        stored = cout if cout is not None else rows
+        assert stored % 16 == 0, (label, stored)
+        self.ops.append(Op(_lib.OP_CONV, src, dst, stored, k, stride, relu, up, up_cout, res, parts, 0, label))
+
+    def simple(self, name, src, dst, cout, k=1, stride=1, relu=1, res=None, cin_logical=None):
+        cin = src[2] if cin_logical is None else cin_logical
+        self.conv(name, src, dst, [Part(name, 0, cout, [(0, 0, cin)])], k, stride, relu, res)
+
+    def csp(self, name, src, dst, cout, n, hid, ci, res_):
+        """YoloNASCSPLayer; physical concat [a | b | b1..bn] (ci) or [a->bn | b]."""
+        R = res_
+        cat = self.buf(name + ".cat", R, hid * (2 + (n if ci else 0)))
+        tmp = self.buf(name + ".tmp", R, hid)
+        self.conv(name + ".conv1|conv2", src, (cat, 0),
+                  [Part(name + ".conv1", 0, hid, [(0, 0, src[2])]), Part(name + ".conv2", hid, hid, [(0, 0, src[2])])])
+        if ci:
+            t = (cat, 0)
+            for j in range(n):
+                self.simple(f"{name}.b{j}.cv1", (t[0], t[1], hid), (tmp, 0), hid, k=3)
+                o = (cat, (2 + j) * hid)
+                self.simple(f"{name}.b{j}.cv2", (tmp, 0, hid), o, hid, k=3, res=(t[0], t[1], f"{name}.b{j}.alpha"))
+                t = o
+            segs = [(0, 0, hid), (hid, (n + 1) * hid, hid)] + [((1 + j) * hid, j * hid, hid) for j in range(1, n + 1)]
+            self.conv(name + ".conv3", (cat, 0, hid * (2 + n)), dst, [Part(name + ".conv3", 0, cout, segs)])
+        else:
+            pp = [self.buf(name + ".t0", R, hid), self.buf(name + ".t1", R, hid)]
+            t = (cat, 0)
+            for j in range(n):
+                self.simple(f"{name}.b{j}.cv1", (t[0], t[1], hid), (tmp, 0), hid, k=3)
+                o = (cat, 0) if j == n - 1 else (pp[j % 2], 0)
+                self.simple(f"{name}.b{j}.cv2", (tmp, 0, hid), o, hid, k=3, res=(t[0], t[1], f"{name}.b{j}.alpha"))
+                t = o
+            self.simple(name + ".conv3", (cat, 0, 2 * hid), dst, cout)
+
+
+def build_plan(image_size: int = 640) -> Plan:
+    P = Plan(image_size)
+    S = image_size
+    stem = P.buf("stem", S // 2, 64)
+    P.ops.append(Op(_lib.OP_STEM, (0, 0, 3), (stem, 0), 64, 3, 2, 1, label="stem"))
+    prev, prev_c, res = stem, 64, S // 2
+    feats = []
+    for i, (cout, n, hid) in enumerate(BACKBONE, start=1):
+        res //= 2
+        down = P.buf(f"stage{i}.down", res, cout)
+        logical_cin = STEM_OUT if i == 1 else prev_c
+        P.conv(f"stage{i}.down", (prev, 0, prev_c), (down, 0), [Part(f"stage{i}.down", 0, cout, [(0, 0, logical_cin)])], k=3, stride=2)
+        out = P.buf(f"c{i + 1}" if i < 4 else "stage4.out", res, cout)
+        P.csp(f"stage{i}.csp", (down, 0, cout), (out, 0), cout, n, hid, True, res)
+        feats.append((out, cout, res))
+        prev, prev_c = out, cout
+    (c2, c2c, r4), (c3, c3c, r8), (c4, c4c, r16), (c5s, c5c, r32) = feats
+    spp = P.buf("spp.cat", r32, 4 * 384)
+    P.simple("spp.cv1", (c5s, 0, 768), (spp, 0), 384)
+    P.ops.append(Op(_lib.OP_SPP, (spp, 0, 384), (spp, 384), 0, label="spp.pool"))
+    c5 = P.buf("c5", r32, 768)
+    P.simple("spp.cv2", (spp, 0, 1536), (c5, 0), 768)
+
+    n3_in = P.buf("neck3.in", r16, 192)   # [down(96) | i2(96)]
+    n4_in = P.buf("neck4.in", r32, 384)   # [down(192) | i1(192)]
+
+    def up_stage(name, low, low_c, low_res, s1, s1c, s2, s2c, inter_dst, out_name):
+        out, n, hid = NECKS[name]
+        R = low_res * 2
+        P.simple(name + ".reduce", (low, 0, low_c), inter_dst, out)
+        fuse = P.buf(name + ".fuse_in", R, 3 * out)
+        P.conv(name + ".up", (inter_dst[0], inter_dst[1], out), (fuse, 0),
+               [Part(name + ".up", 0, 4 * out, [(0, 0, out)], transposed=True)], relu=0, up=1, up_cout=out)
+        P.simple(name + ".skip1", (s1, 0, s1c), (fuse, out), out)
+        s2r = P.buf(name + ".s2r", R * 2, out)
+        P.simple(name + ".skip2_reduce", (s2, 0, s2c), (s2r, 0), out)
+        P.simple(name + ".skip2_down", (s2r, 0, out), (fuse, 2 * out), out, k=3, stride=2)
+        y = P.buf(name + ".y", R, out)
+        P.simple(name + ".fuse", (fuse, 0, 3 * out), (y, 0), out)
+        o = P.buf(out_name, R, out)
+        P.csp(name + ".csp", (y, 0, out), (o, 0), out, n, hid, False, R)
+        return o
+
+    x = up_stage("neck1", c5, 768, r32, c4, c4c, c3, c3c, (n4_in, 192), "neck1.out")
+    p3 = up_stage("neck2", x, 192, r16, c3, c3c, c2, c2c, (n3_in, 96), "p3")
+    P.simple("neck3.down", (p3, 0, 96), (n3_in, 0), 96, k=3, stride=2)
+    p4 = P.buf("p4", r16, 192)
+    P.csp("neck3.csp", (n3_in, 0, 192), (p4, 0), 192, NECKS["neck3"][1], NECKS["neck3"][2], False, r16)
+    P.simple("neck4.down", (p4, 0, 192), (n4_in, 0), 192, k=3, stride=2)
+    p5 = P.buf("p5", r32, 384)
+    P.csp("neck4.csp", (n4_in, 0, 384), (p5, 0), 384, NECKS["neck4"][1], NECKS["neck4"][2], False, r32)
+
+    for l, ((cin, bb, stride), feat) in enumerate(zip(HEADS, (p3, p4, p5)), start=1):
+        h, R = f"head{l}", S // stride
+        st = P.buf(h + ".stems", R, bb + FLAME_INTER)
+        P.conv(h + ".stems", (feat, 0, cin), (st, 0),
+               [Part(h + ".bbox_stem", 0, bb, [(0, 0, cin)]), Part(h + ".pose_stem", bb, FLAME_INTER, [(0, 0, cin)])])
+        cr = P.buf(h + ".clsreg", R, 2 * bb)
+        P.conv(h + ".cls|reg", (st, 0, bb), (cr, 0),
+               [Part(h + ".cls_conv", 0, bb, [(0, 0, bb)]), Part(h + ".reg_conv", bb, bb, [(0, 0, bb)])], k=3)
+        reg = P.buf(h + ".reg_raw", R, REG_ROWS, fp32=1)
+        P.conv(h + ".preds", (cr, 0, 2 * bb), (reg, 0),
+               [Part(h + ".reg_pred", 0, 68, [(bb, 0, bb)]), Part(h + ".cls_pred", 68, 1, [(0, 0, bb)])], relu=0, cout=REG_ROWS)
+        P.reg_buf.append(reg)
+        t_prev = P.buf(h + ".t0", R, 512)
+        parts, row = [], 0
+        for tower, inter, _ in TOWERS:
+            parts.append(Part(f"{h}.{tower}.0", row, inter, [(0, 0, FLAME_INTER)]))
+            row += inter
+        P.conv(h + ".towers0", (st, bb, FLAME_INTER), (t_prev, 0), parts, k=3)
+        for i in (1, 2):
+            t_next = P.buf(f"{h}.t{i}", R, 512)
+            P.simple(f"{h}.shape.{i}", (t_prev, 0, 256), (t_next, 0), 256, k=3)
+            P.simple(f"{h}.expr.{i}", (t_prev, 256, 128), (t_next, 256), 128, k=3)
+            P.conv(f"{h}.transf.{i}", (t_prev, 384, 128), (t_next, 384),
+                   [Part(f"{h}.{tw}.{i}", 32 * q, 32, [(32 * q, 0, 32)]) for q, tw in enumerate(("rot", "jaw", "scale", "transl"))], k=3)
+            t_prev = t_next
+        fl = P.buf(h + ".flame_raw", R, FLAME_ROWS, fp32=1)
+        col = {"shape": (0, 256), "expr": (256, 128), "rot": (384, 32), "jaw": (416, 32), "scale": (448, 32), "transl": (480, 32)}
+        P.conv(h + ".flame_out", (t_prev, 0, 512), (fl, 0),
+               [Part(f"{h}.{tw}.out", RAW_ROW_OFF[tw], oc, [(col[tw][0], 0, col[tw][1])]) for tw, _, oc in TOWERS],
+               relu=0, cout=FLAME_ROWS)
+        P.flame_buf.append(fl)
+    return P
+
+
+def _auto_block_n(cout: int, up: int, up_cout: int) -> int:
+    lim = up_cout if up else cout
+    if lim <= 256:
+        return lim
+    for n in range(256, 15, -16):
+        if lim % n == 0:
+            return n
+    return 16
+
+
+@dataclass
+class PackedNet:
+    plan: Plan
+    weights: np.ndarray   # uint16 bf16 bits
+    bias: np.ndarray      # float32
+    stem_w: np.ndarray    # [48,27] float32
+    stem_b: np.ndarray    # [48]
+    op_meta: List[dict]
+
+
+def pack(plan: Plan, w: Dict[str, torch.Tensor]) -> PackedNet:
+    """Pack deploy-form weights ({name}.w [Cout,Cin,k,k], {name}.b) for the plan."""
+    wchunks, bchunks, meta = [], [], []
+    w_off = b_off = 0
+    for op in plan.ops:
+        if op.kind != _lib.OP_CONV:
+            meta.append({})
+            continue
+        cin, taps = op.src[2], op.k * op.k
+        block_n = _auto_block_n(op.cout, op.up, op.up_cout)
+        n_pad = (op.cout + block_n - 1) // block_n * block_n
+        M = torch.zeros(n_pad, taps, cin, dtype=torch.float32)
+        bvec = torch.zeros(n_pad, dtype=torch.float32)
+        for p in op.parts:
+            wt, bt = w[p.name + ".w"].float(), w[p.name + ".b"].float()
+            if p.transposed:  # ConvTranspose2d weight [Cin, Cout, 2, 2]; row = (dy*2+dx)*Cout + co
+                co = wt.shape[1]
+                for dy in range(2):
+                    for dx in range(2):
+                        sub = dy * 2 + dx
+                        M[sub * co:(sub + 1) * co, 0, :] = wt[:, :, dy, dx].T
+                        bvec[sub * co:(sub + 1) * co] = bt
+                continue
+            assert wt.shape[0] == p.cout and wt.shape[2] == op.k, (p.name, tuple(wt.shape), p.cout, op.k)
+            assert sum(s[2] for s in p.segs) == wt.shape[1], (p.name, p.segs, wt.shape)
+            wk = wt.permute(0, 2, 3, 1).reshape(p.cout, taps, wt.shape[1])  # [co][tap][ci]
+            for phys, log, n in p.segs:
+                M[p.row:p.row + p.cout, :, phys:phys + n] = wk[:, :, log:log + n]
+            bvec[p.row:p.row + p.cout] = bt
+        alpha = float(w[op.res[2]]) if op.res is not None else 0.0
+        chunk = M.reshape(-1).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+        pad = (-chunk.size) % 64  # keep every TMA base address 128-byte aligned
+        if pad:
+            chunk = np.concatenate([chunk, np.zeros(pad, dtype=np.uint16)])
+        wchunks.append(chunk)
+        bchunks.append(bvec.numpy())
+        meta.append(dict(w_off=w_off, b_off=b_off, n_pad=n_pad, k_total=taps * cin, block_n=block_n, alpha=alpha))
+        w_off += chunk.size
+        b_off += n_pad
+    sw = w["stem.w"].float().permute(0, 2, 3, 1).reshape(STEM_OUT, 27) / 255.0  # (ky,kx,c); detector.py:51 folded
+    return PackedNet(plan, np.concatenate(wchunks), np.concatenate(bchunks), np.ascontiguousarray(sw.numpy()),
+                     np.ascontiguousarray(w["stem.b"].float().numpy()), meta)
+
+
+def conv_names() -> List[Tuple[str, int, int, int, bool]]:
+    """(name, k, cin, cout, is_transpose) of the 191 deploy-form convs, derived from the plan."""
+    out = [("stem", 3, 3, STEM_OUT, False)]
+    for op in build_plan(640).ops:
+        for p in op.parts:
+            cin = sum(s[2] for s in p.segs)
+            out.append((p.name, 2 if p.transposed else op.k, cin, p.cout // 4 if p.transposed else p.cout, p.transposed))
+    return out
+
+
+def synthetic_weights(seed: int = 0, bias_std: float = 0.02) -> Dict[str, torch.Tensor]:
+    """Seeded random-init deploy-form weights (no checkpoint is reachable offline): He-normal,
+    second-moment preserving through the residual bottlenecks (alpha 0.5, cv2 gain 1), pred convs
+    gain 1, cls_pred.bias = -log(99) (yolo_head_dfl_head.py:188-190)."""
+    g = torch.Generator().manual_seed(seed)
+    w: Dict[str, torch.Tensor] = {}
+    for name, k, cin, cout, tr in conv_names():
+        if tr:
+            w[name + ".w"] = torch.randn(cin, cout, 2, 2, generator=g) * math.sqrt(1.0 / cin)
+        else:
+            lin = name.endswith("_pred") or name.endswith(".out") or (name.endswith(".cv2") and ".csp.b" in name)
+            w[name + ".w"] = torch.randn(cout, cin, k, k, generator=g) * math.sqrt((1.0 if lin else 2.0) / (cin * k * k))
+        w[name + ".b"] = torch.randn(cout, generator=g) * bias_std
+        if name.endswith(".cls_pred"):
+            w[name + ".b"] = torch.full((cout,), -math.log(99.0))
+        if name.endswith(".cv2") and ".csp.b" in name:
+            w[name[:-4] + ".alpha"] = torch.tensor(0.5)
+    return w
+
+
+def total_macs(image_size: int = 640) -> int:
+    """Algorithmic MACs per image of the deploy-form network (83.34 G @640)."""
+    P = build_plan(image_size)
+    tot = 3 * STEM_OUT * 9 * (image_size // 2) ** 2
+    for op in P.ops:
+        if op.kind != _lib.OP_CONV:
+            continue
+        src_res = P.bufs[op.src[0]][0]
+        out_res = src_res if op.up else src_res // op.stride
+        for p in op.parts:
+            cin = sum(s[2] for s in p.segs)
+            tot += cin * p.cout * out_res * out_res * (1 if p.transposed else op.k * op.k)
+    return tot

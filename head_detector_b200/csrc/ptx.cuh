@@ -2,6 +2,7 @@
 // alloc/ld, commit, fences).  Hand-written; no CUTLASS/CuTe in the build.
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -48,8 +49,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Bounded wait: a pipeline bug (wrong expect_tx, bad descriptor) must surface as a trapped launch,
+// never as a hung GPU.  ~4e9 SM cycles is seconds; a healthy wait is microseconds.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) {
+      printf("vgh: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+      __trap();
+    }
   }
 }
 

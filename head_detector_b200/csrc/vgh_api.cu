@@ -331,6 +331,60 @@ static int run_post(vgh_detector* d, float conf, float iou, int top_k, const flo
   return 0;
 }
 
+// Eager execution with one CUDA-event pair around every plan op and every post-processing stage.
+extern "C" int vgh_detector_profile(vgh_detector* d, int iters, float conf_thr, float iou_thr, int top_k,
+                                    float* ms_out, int capacity, void* stream) {
+  if (!d || !ms_out || iters < 1) return fail(1, "bad argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int n_ops = static_cast<int>(d->ops.size());
+  const int n = n_ops + 4;
+  if (capacity < n) return fail(1, "ms_out capacity %d < %d", capacity, n);
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) CUDA_OK(cudaEventCreate(&e));
+  std::vector<double> acc(n, 0.0);
+  int rc = 0;
+  for (int it = 0; it < iters && !rc; ++it) {
+    CUDA_OK(cudaEventRecord(ev[0], s));
+    for (int i = 0; i < n_ops && !rc; ++i) {
+      OpRt& o = d->ops[i];
+      if (o.d.kind == VGH_OP_STEM)
+        rc = stem_conv_launch(d->input, d->stem_w, d->stem_b, static_cast<__nv_bfloat16*>(d->buf_ptr[o.d.out_buf]), d->B, d->S, s);
+      else if (o.d.kind == VGH_OP_CONV)
+        rc = conv_launch(o.L, o.bk, s);
+      else
+        rc = spp_pool_launch(static_cast<__nv_bfloat16*>(d->buf_ptr[o.d.in_buf]), d->B, d->bufs[o.d.in_buf].H, d->bufs[o.d.in_buf].W, o.d.cin, s);
+      CUDA_OK(cudaEventRecord(ev[i + 1], s));
+    }
+    if (rc) break;
+    rc = box_decode_launch(d->lv, d->boxes, d->scores, d->B, d->A, s);
+    if (d->ovr_boxes && d->ovr_scores) {
+      cudaMemcpyAsync(d->boxes, d->ovr_boxes, sizeof(float) * 4 * d->B * d->A, cudaMemcpyDeviceToDevice, s);
+      cudaMemcpyAsync(d->scores, d->ovr_scores, sizeof(float) * d->B * d->A, cudaMemcpyDeviceToDevice, s);
+    }
+    CUDA_OK(cudaEventRecord(ev[n_ops + 1], s));
+    if (!rc) rc = select_nms_launch(d->boxes, d->scores, d->B, d->A, conf_thr, iou_thr, top_k, d->keep_k, d->keep_idx, d->keep_cnt,
+                                    d->keep_boxes, d->keep_scores, s, g_err, sizeof(g_err));
+    CUDA_OK(cudaEventRecord(ev[n_ops + 2], s));
+    if (!rc) rc = flame_gather_launch(d->lv, d->keep_idx, d->keep_cnt, d->B, d->keep_k, d->img_xform, d->offsets, d->offsets + d->B,
+                                      d->params, d->head_xform, d->head_img, s);
+    CUDA_OK(cudaEventRecord(ev[n_ops + 3], s));
+    if (!rc && d->flame)
+      rc = flame_decode_launch(d->flame->model, d->params, d->B * d->keep_k, d->offsets + d->B, 128, 64, d->head_xform, nullptr,
+                               d->rot, d->verts, s, g_err, sizeof(g_err));
+    CUDA_OK(cudaEventRecord(ev[n_ops + 4], s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    for (int i = 0; i < n; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+      acc[i] += ms;
+    }
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  if (rc) return rc > 0 && g_err[0] ? rc : fail(5, "profile launch failed");
+  for (int i = 0; i < n; ++i) ms_out[i] = static_cast<float>(acc[i] / iters);
+  return 0;
+}
+
 extern "C" int vgh_detector_forward(vgh_detector* d, const uint8_t* images_dev, void* stream) {
   if (!d || !images_dev) return fail(1, "null argument");
   return run_forward(d, images_dev, static_cast<cudaStream_t>(stream), nullptr);

@@ -1,0 +1,121 @@
+"""`HeadDetector` with the reference's constructor and call signature
+(head_detector/detector.py:18-102), running on the B200 engine.
+
+    HeadDetector(model="vgg_heads_l", image_size=640)(image, confidence_threshold=0.5)
+        -> PredictionResult with .heads[i].bbox / .score / .flame_params / .vertices_3d / .head_pose
+
+Differences that are extensions, not changes: `weights=` (a deploy-form weight dict or a path to a
+torch-saved one; the HF download of detector.py:25-30 is impossible offline), `batch_size=` and
+`detect_batch()` (batched semantics of yolo_heads_post_prediction_callback.py:55-97)."""
+import os
+import warnings
+from typing import Any, Dict, List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import arch
+from .detection_result import PredictionResult
+from .engine import Engine
+from .flame import FLAMELayer
+from .head_info import Bbox, FlameParams, HeadMetadata
+from .utils import rpy_from_rotations
+
+
+class HeadDetector:
+    def __init__(self, model: str = "vgg_heads_l", image_size: int = 640, weights: Union[None, str, Dict[str, torch.Tensor]] = None,
+                 batch_size: int = 1, keep_top_k: int = 100):
+        if not torch.cuda.is_available():
+            raise RuntimeError("head_detector_b200.HeadDetector needs a CUDA device (sm_100a); there is no CPU fallback")
+        self._image_size = image_size
+        self._device = torch.device("cuda")
+        self._flame = FLAMELayer()
+        self._batch = batch_size
+        self._keep_top_k = keep_top_k
+        self.model = self._read_model(model, weights)
+
+    def _read_model(self, model: str, weights=None) -> Engine:
+        if model != "vgg_heads_l":
+            raise ValueError(f"unknown model {model!r}; only 'vgg_heads_l' (YoloHeads_L) is built")
+        if weights is None:
+            weights = os.environ.get("VGGHEADS_B200_WEIGHTS")
+        if isinstance(weights, str):
+            weights = torch.load(weights, map_location="cpu")
+        if weights is None:
+            warnings.warn("no weights given and the released vgg_heads_l checkpoint is unreachable offline: "
+                          "using seeded random-init weights (architecture and cost are exact, detections are not meaningful)")
+            weights = arch.synthetic_weights(0)
+        return Engine(weights, self._batch, self._image_size, self._keep_top_k, self._flame)
+
+    # -- host-side pre-processing, same arithmetic as detector.py:32-56
+    def _convert_image(self, image) -> np.ndarray:
+        if isinstance(image, str):
+            import cv2
+
+            image = cv2.cvtColor(cv2.imread(image), cv2.COLOR_BGR2RGB)
+        elif not isinstance(image, np.ndarray):
+            image = np.array(image)
+        return image
+
+    def _transform_image(self, image: np.ndarray) -> Tuple[np.ndarray, Tuple[int, int], float]:
+        import cv2
+
+        S = self._image_size
+        h, w = image.shape[:2]
+        new_h, new_w = (S, int(w * S / h)) if h > w else (int(h * S / w), S)
+        scale = S / max(h, w)
+        if (new_h, new_w) != (h, w):
+            image = cv2.resize(image, (new_w, new_h), interpolation=cv2.INTER_LANCZOS4)
+        pad_w, pad_h = S - image.shape[1], S - image.shape[0]
+        if pad_w or pad_h:
+            image = cv2.copyMakeBorder(image, pad_h // 2, pad_h - pad_h // 2, pad_w // 2, pad_w - pad_w // 2,
+                                       cv2.BORDER_CONSTANT, value=127)
+        return np.ascontiguousarray(image[..., :3], dtype=np.uint8), (pad_w // 2, pad_h // 2), scale
+
+    # -- batched device path
+    def detect_batch(self, images_u8: torch.Tensor, confidence_threshold: float = 0.5, img_xform: Optional[torch.Tensor] = None):
+        """uint8 [B,S,S,3] (cuda) -> dict of device tensors: keep_cnt, keep_boxes, keep_scores, offsets,
+        params [N,413], vertices [N,5023,3], rotations [N,3,3] (N = total heads, image-major)."""
+        eng = self.model
+        eng.forward(images_u8.to(self._device))
+        eng.postprocess(confidence_threshold, 0.5, 1000, img_xform)
+        n = int(eng.head_offsets[-1])
+        return {"keep_cnt": eng.keep_cnt, "keep_boxes": eng.keep_boxes, "keep_scores": eng.keep_scores,
+                "offsets": eng.head_offsets, "params": eng.head_params(n), "vertices": eng.head_verts(n),
+                "rotations": eng.head_rot(n)}
+
+    def _parse_predictions(self, out: Dict[str, torch.Tensor], img: int, cache: Dict[str, Any]) -> List[HeadMetadata]:
+        """detector.py:61-90 for image `img` of the batch."""
+        pad, scale, S = cache["padding"], cache["scale"], self._image_size
+        lo, hi = int(out["offsets"][img]), int(out["offsets"][img + 1])
+        n = hi - lo
+        boxes = out["keep_boxes"][img, :n].cpu().numpy()
+        scores = out["keep_scores"][img, :n].cpu().numpy()
+        verts = out["vertices"][lo:hi].cpu().numpy()          # already un-padded / un-scaled on the device
+        params = out["params"][lo:hi].cpu()
+        rots = out["rotations"][lo:hi].cpu().numpy()
+        boxes = boxes.clip(0, S)
+        boxes[:, [0, 2]] -= pad[0]
+        boxes[:, [1, 3]] -= pad[1]
+        boxes /= scale
+        boxes = np.rint(boxes).astype(int)
+        poses = rpy_from_rotations(rots)
+        heads = []
+        for i in range(n):
+            fp = FlameParams.from_3dmm(params[i:i + 1])
+            fp.scale = fp.scale / scale
+            b = boxes[i]
+            heads.append(HeadMetadata(bbox=Bbox(x=b[0], y=b[1], w=b[2] - b[0], h=b[3] - b[1]), score=scores[i],
+                                      flame_params=fp, vertices_3d=verts[i], head_pose=poses[i]))
+        return heads
+
+    def __call__(self, image, confidence_threshold: float = 0.5) -> PredictionResult:
+        original = self._convert_image(image)
+        img, padding, scale = self._transform_image(original)
+        batch = torch.from_numpy(img)[None].to(self._device)
+        if self._batch != 1:
+            batch = batch.expand(self._batch, -1, -1, -1).contiguous()
+        xf = torch.tensor([[padding[0], padding[1], scale]] * self._batch, dtype=torch.float32)
+        out = self.detect_batch(batch, confidence_threshold, xf)
+        heads = self._parse_predictions(out, 0, {"padding": padding, "scale": scale})
+        return PredictionResult(original_image=original, heads=heads)

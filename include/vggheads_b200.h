@@ -151,6 +151,11 @@ int vgh_detector_run_device(vgh_detector* d, float conf_thr, float iou_thr, int 
  * scores [B,A] with caller data (random weights never yield detections).
  * The copy is part of the timed device work.  NULL, NULL disables it. */
 int vgh_detector_set_override(vgh_detector* d, const float* boxes_dev, const float* scores_dev);
+/* Measurement aid: eager (non-graph) execution over the internal staging image with one CUDA-event
+ * pair around every plan op and every post-processing stage, averaged over `iters`.  ms_out
+ * (capacity >= n_ops + 4) = [op_0 .. op_{n-1}, box_decode, select_nms, gather, flame_decode]. */
+int vgh_detector_profile(vgh_detector* d, int iters, float conf_thr, float iou_thr, int top_k, float* ms_out,
+                         int capacity, void* stream);
 /* Number of kernel launches one forward+postprocess issues (graph nodes), for reporting. */
 int vgh_detector_launch_count(const vgh_detector* d);
 

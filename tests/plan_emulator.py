@@ -1,0 +1,71 @@
+"""CPU interpreter of a head_detector_b200.arch plan + packed weights (test infrastructure).
+
+Executes exactly what the CUDA executor is told to do (op list, channel slices, packed K-major
+matrices, residuals, pixel-shuffle) with plain torch ops, so that plan wiring and weight packing
+can be checked against the oracle network on a machine without a GPU."""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from head_detector_b200 import _lib, arch
+
+
+def bf16_round(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def apply_op(pk, op, m, bufs, images_u8=None, emulate_bf16=True):
+    """Execute ONE plan op on the given NHWC float buffers (in place)."""
+    P = pk.plan
+    rnd = bf16_round if emulate_bf16 else (lambda t: t)
+    if op.kind == _lib.OP_STEM:
+        x = images_u8.permute(0, 3, 1, 2).float()
+        w = torch.from_numpy(pk.stem_w).reshape(48, 3, 3, 3).permute(0, 3, 1, 2)
+        y = F.relu(F.conv2d(x, w, torch.from_numpy(pk.stem_b), stride=2, padding=1))
+        bufs[op.dst[0]][..., :48] = rnd(y.permute(0, 2, 3, 1))
+        bufs[op.dst[0]][..., 48:] = 0
+    elif op.kind == _lib.OP_SPP:
+        b = bufs[op.src[0]]
+        C = op.src[2]
+        x = b[..., :C].permute(0, 3, 1, 2)
+        for i, k in enumerate((5, 9, 13), start=1):
+            b[..., i * C:(i + 1) * C] = F.max_pool2d(x, k, 1, k // 2).permute(0, 2, 3, 1)
+    else:
+        sb, so, cin = op.src
+        x = bufs[sb][..., so:so + cin].permute(0, 3, 1, 2)
+        wts = torch.from_numpy(pk.weights[m["w_off"]:m["w_off"] + m["n_pad"] * m["k_total"]].view(np.int16).copy()).view(torch.bfloat16).float()
+        W = wts.reshape(m["n_pad"], op.k, op.k, cin).permute(0, 3, 1, 2)
+        bv = torch.from_numpy(pk.bias[m["b_off"]:m["b_off"] + m["n_pad"]])
+        y = F.conv2d(x, W, bv, stride=op.stride, padding=op.k // 2)[:, :op.cout]
+        if op.relu:
+            y = F.relu(y)
+        if op.res is not None:
+            rb, ro, _ = op.res
+            y = y + m["alpha"] * bufs[rb][..., ro:ro + op.cout].permute(0, 3, 1, 2)
+        y = y.permute(0, 2, 3, 1)
+        db, do = op.dst
+        if not P.bufs[db][3]:
+            y = rnd(y)
+        if op.up:
+            co = op.up_cout
+            for sub in range(4):
+                bufs[db][:, (sub >> 1)::2, (sub & 1)::2, do:do + co] = y[..., sub * co:(sub + 1) * co]
+        else:
+            bufs[db][..., do:do + op.cout] = y
+
+
+def run_plan(pk: arch.PackedNet, images_u8: torch.Tensor, emulate_bf16: bool = True):
+    """images_u8 [B,S,S,3] uint8 -> list of NHWC float buffers."""
+    B = images_u8.shape[0]
+    bufs = [torch.zeros(B, h, w, c) for (h, w, c, _) in pk.plan.bufs]
+    for op, m in zip(pk.plan.ops, pk.op_meta):
+        apply_op(pk, op, m, bufs, images_u8, emulate_bf16)
+    return bufs
+
+
+def raw_to_oracle_layout(pk, bufs, level):
+    """reg [B,68,H,W], cls [B,1,H,W], towers dict as the oracle's head_level returns them."""
+    reg = bufs[pk.plan.reg_buf[level]].permute(0, 3, 1, 2)
+    fl = bufs[pk.plan.flame_buf[level]].permute(0, 3, 1, 2)
+    t = {tw: fl[:, arch.RAW_ROW_OFF[tw]:arch.RAW_ROW_OFF[tw] + oc] for tw, _, oc in arch.TOWERS}
+    return reg[:, :68], reg[:, 68:69], t

@@ -1,0 +1,141 @@
+"""Conv network on the GPU (tcgen05 implicit GEMM + aux kernels) vs the CPU interpretation of the
+same plan and vs the oracle network.  bf16 storage => comparisons allow bf16 rounding flips:
+|err| <= 2^-6 * max|ref| per buffer and a mean error two orders below that."""
+import numpy as np
+import pytest
+import torch
+
+import plan_emulator as pe
+from oracle import nms_oracle, flame_oracle, net_oracle as no
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def small():
+    from head_detector_b200.engine import Engine
+
+    S, B = 128, 2
+    w = no.synthetic_weights(3)
+    eng = Engine(w, B, S)
+    torch.manual_seed(0)
+    img = torch.randint(0, 256, (B, S, S, 3), dtype=torch.uint8)
+    eng.forward(img.cuda())
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = pe.run_plan(eng.packed, img, emulate_bf16=True)
+    return eng, img, ref, w
+
+
+def test_every_buffer_matches_cpu_interpretation(small):
+    eng, img, ref, _ = small
+    bad = []
+    for name, i in eng.plan.buf_names.items():
+        got, want = eng.read_buffer(name), ref[i]
+        scale = want.abs().max().item() + 1e-6
+        err = (got - want).abs()
+        if not (err.max().item() <= 2 ** -6 * scale + 1e-5 and err.mean().item() <= 2e-3 * scale):
+            bad.append((name, err.max().item(), err.mean().item(), scale))
+    assert not bad, bad
+
+
+def test_decode_kernels_vs_oracle_decode(small):
+    """boxes / scores / dense flame from the GPU's own raw head outputs (stage-wise, same inputs)."""
+    eng, _, _, _ = small
+    raw = []
+    for l in range(3):
+        reg = eng.read_buffer(f"head{l + 1}.reg_raw").permute(0, 3, 1, 2)
+        fl = eng.read_buffer(f"head{l + 1}.flame_raw").permute(0, 3, 1, 2)
+        from head_detector_b200 import arch
+        raw.append((reg[:, :68], reg[:, 68:69], {tw: fl[:, arch.RAW_ROW_OFF[tw]:arch.RAW_ROW_OFF[tw] + oc] for tw, _, oc in arch.TOWERS}))
+    boxes, scores, flame = no.decode_heads(raw)
+    assert (eng.boxes.cpu() - boxes).abs().max() < 1e-3
+    assert (eng.scores.cpu() - scores[..., 0]).abs().max() < 1e-6
+    dense = eng.dense_flame().cpu()
+    assert dense.shape == flame.shape
+    rel = (dense - flame).abs() / (flame.abs() + 1.0)
+    assert rel.max() < 1e-5
+
+
+def test_end_to_end_vs_oracle_network_640():
+    """Whole network at the reference resolution vs the oracle with bf16-rounded weights/activations."""
+    from head_detector_b200.engine import Engine
+
+    w = no.synthetic_weights(0)
+    eng = Engine(w, 1, 640)
+    torch.manual_seed(1)
+    img = torch.randint(0, 256, (1, 640, 640, 3), dtype=torch.uint8)
+    boxes, scores = eng.forward(img.cuda())
+    dense = eng.dense_flame().cpu()
+    wq = {k: (v.to(torch.bfloat16).float() if k.endswith(".w") and not k.startswith("stem") else v) for k, v in w.items()}
+    with torch.no_grad():
+        ob, os_, of = no.DeployNet(wq, act_round=pe.bf16_round).forward(img.permute(0, 3, 1, 2).float() / 255)
+    assert eng.A == 8400 and boxes.shape == (1, 8400, 4)
+    assert (boxes.cpu() - ob).abs().max() < 1.0            # pixels, boxes span ~[-300, 900]
+    assert (boxes.cpu() - ob).abs().mean() < 0.05
+    assert (scores.cpu() - os_[..., 0]).abs().max() < 2e-3
+    assert (dense[..., :400] - of[..., :400]).abs().max() < 0.1     # 3*tanh outputs
+    rel_scale = ((dense[..., 412] - of[..., 412]).abs() / of[..., 412]).max()
+    assert rel_scale < 0.05
+
+
+def test_pipeline_stagewise_parity_and_host_path():
+    """forward -> (engineered scores) -> select/NMS -> survivor rows -> FLAME: NMS ids bit-exact vs
+    the oracle on the same boxes/scores, vertices within 1e-4 of the oracle on the same rows, and
+    the host-buffer graph path returns the same numbers as the staged path."""
+    from head_detector_b200.engine import Engine
+    from oracle.make_golden import clustered_anchors
+
+    B, S = 3, 640
+    eng = Engine(no.synthetic_weights(0), B, S)
+    torch.manual_seed(2)
+    img = torch.randint(0, 256, (B, S, S, 3), dtype=torch.uint8)
+    ob, osc = zip(*[clustered_anchors(8400, 8, 12, seed=50 + i) for i in range(B)])
+    ob, osc = torch.stack(ob).cuda(), torch.stack(osc).cuda()
+    eng.set_override(ob, osc)
+    xf = torch.tensor([[0., 0., 1.0], [0., 80., 0.5], [16., 0., 0.8]])
+    eng.forward(img.cuda())
+    eng.boxes.copy_(ob); eng.scores.copy_(osc)     # staged path: apply the override by hand
+    eng.postprocess(0.5, 0.5, 1000, xf.cuda())
+    torch.cuda.synchronize()
+    cnt = eng.keep_cnt.cpu().numpy()
+    idx = eng.keep_idx.cpu().numpy()
+    off = eng.head_offsets.cpu().numpy()
+    dense = eng.dense_flame().cpu()
+    consts = flame_oracle.load_flame_constants()
+    total = int(off[-1])
+    assert total == cnt.sum() and total > 0
+    params, verts = eng.head_params(total).cpu(), eng.head_verts(total).cpu()
+    for b in range(B):
+        want = nms_oracle.select_nms(ob[b].cpu().numpy(), osc[b].cpu().numpy())
+        assert idx[b, :cnt[b]].tolist() == want.tolist()
+        rows = params[off[b]:off[b + 1]]
+        assert torch.equal(rows, dense[b][torch.from_numpy(want)])
+        ref = flame_oracle.detector_vertices(rows, consts, (xf[b, 0].item(), xf[b, 1].item()), xf[b, 2].item())
+        assert (verts[off[b]:off[b + 1]] - ref).abs().max() < 1e-4 / xf[b, 2].item()
+    # host-buffer end-to-end (CUDA graph) must reproduce the staged results
+    out = eng.alloc_host_outputs(B * 100)
+    n = eng.run_host(img.pin_memory(), out, 0.5, 0.5, 1000, xf.pin_memory())
+    assert n == total and out["keep_cnt"].numpy().tolist() == cnt.tolist()
+    assert torch.equal(out["params"][:n], params) and torch.equal(out["verts"][:n], verts)
+    assert eng.launch_count > 100
+
+
+def test_head_detector_call_api():
+    """`HeadDetector()(image)` -> PredictionResult with the reference's fields (random weights: the
+    engineered-score override provides heads)."""
+    import head_detector_b200
+    from oracle.make_golden import clustered_anchors
+
+    det = head_detector_b200.HeadDetector(weights=no.synthetic_weights(0))
+    ob, osc = clustered_anchors(8400, 4, 10, seed=5)
+    det.model.set_override(ob[None].cuda(), osc[None].cuda())
+    rng = np.random.default_rng(0)
+    image = rng.integers(0, 256, (480, 640, 3), dtype=np.uint8)     # letterboxed: pad (0, 80), scale 1.0
+    res = det(image, confidence_threshold=0.5)
+    want = nms_oracle.select_nms(ob.numpy(), osc.numpy())
+    assert len(res.heads) == len(want) > 0
+    h = res.heads[0]
+    assert h.vertices_3d.shape == (5023, 3) and h.vertices_3d.dtype == np.float32
+    assert h.flame_params.rotation.shape == (1, 6) and len(h.bbox) == 4 and -180 <= h.head_pose.yaw <= 180
+    assert "num heads" in repr(res)

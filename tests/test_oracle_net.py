@@ -1,0 +1,78 @@
+"""Self-consistency of the conv-network oracle (parity unpinned at the super_gradients boundary)
+and of the product's execution plan / weight packing against it - all on CPU."""
+import numpy as np
+import torch
+
+import plan_emulator as pe
+from head_detector_b200 import arch
+from oracle import net_oracle as no
+
+
+def test_layer_enumeration_matches_survey():
+    assert len(no.conv_layer_list()) == 191
+    assert abs(no.total_macs(640) / 1e9 - 83.341) < 0.001
+    assert abs(no.total_macs(1280) / no.total_macs(640) - 4.0) < 1e-9
+    assert arch.total_macs(640) == no.total_macs(640)
+    assert len(arch.conv_names()) == 191
+    assert {n for n, *_ in arch.conv_names()} == {n for n, *_ in no.conv_layer_list()}
+
+
+def test_qarepvgg_fold_exact_in_fp64():
+    g = torch.Generator().manual_seed(0)
+    for cin, cout, stride, residual, alpha in [(16, 16, 1, True, False), (8, 24, 2, False, False), (12, 12, 1, False, True)]:
+        m = no.QARepVGGUnfused(cin, cout, stride, residual, alpha).double().eval()
+        for bn in (m.bn3, m.post_bn):
+            no.randomize_bn_(bn, g)
+        if alpha:
+            m.alpha.data.fill_(0.7)
+        x = torch.randn(2, cin, 10, 10, generator=g, dtype=torch.float64)
+        w, b = no.fold_qarepvgg(m)
+        with torch.no_grad():
+            ref = m(x)
+        got = torch.relu(torch.nn.functional.conv2d(x, w, b, stride=stride, padding=1))
+        assert (ref - got).abs().max() < 1e-12
+
+
+def test_anchor_count_and_order():
+    pts, strides = no.anchor_points([(80, 80), (40, 40), (20, 20)])
+    assert pts.shape == (8400, 2) and strides[0] == 8 and strides[-1] == 32
+    assert pts[0].tolist() == [0.5, 0.5] and pts[1].tolist() == [1.5, 0.5] and pts[80].tolist() == [0.5, 1.5]
+
+
+def test_plan_and_packing_reproduce_oracle():
+    """Interpret the product's plan with its packed bf16 weights on CPU; compare with the oracle."""
+    S = 128
+    w = no.synthetic_weights(3)
+    pk = arch.pack(arch.build_plan(S), w)
+    torch.manual_seed(0)
+    img = torch.randint(0, 256, (2, S, S, 3), dtype=torch.uint8)
+    wq = {k: (v.to(torch.bfloat16).float() if k.endswith(".w") and not k.startswith("stem") else v) for k, v in w.items()}
+    taps = {}
+    with torch.no_grad():
+        no.DeployNet(wq).forward(img.permute(0, 3, 1, 2).float() / 255, taps)
+        bufs = pe.run_plan(pk, img, emulate_bf16=False)
+    for l in range(3):
+        reg, cls, t = pe.raw_to_oracle_layout(pk, bufs, l)
+        oreg, ocls, ot = taps["raw"][l]
+        assert (reg - oreg).abs().max() < 1e-4 and (cls - ocls).abs().max() < 1e-4
+        for k in t:
+            assert (t[k] - ot[k]).abs().max() < 1e-4, k
+    for name in ("c2", "c3", "c4", "c5", "p3", "p4", "p5"):
+        assert (bufs[pk.plan.buf_names[name]].permute(0, 3, 1, 2) - taps[name]).abs().max() < 1e-4
+
+
+def test_decode_channel_rotation():
+    """o[400:409] = [c[403:409], c[400:403]] (bug-compatible layout)."""
+    H = [(2, 2), (1, 1), (1, 1)]
+    raw = []
+    for h, w in H:
+        t = {"shape": torch.zeros(1, 128, h, w), "expr": torch.zeros(1, 64, h, w), "rot": torch.arange(6.).view(1, 6, 1, 1).expand(1, 6, h, w) + 10,
+             "jaw": torch.arange(3.).view(1, 3, 1, 1).expand(1, 3, h, w) + 20, "scale": torch.zeros(1, 1, h, w), "transl": torch.zeros(1, 3, h, w)}
+        raw.append((torch.zeros(1, 68, h, w), torch.zeros(1, 1, h, w), t))
+    boxes, scores, fl = no.decode_heads(raw)
+    assert fl.shape == (1, 6, 413)
+    assert fl[0, 0, 400:409].tolist() == [13, 14, 15, 20, 21, 22, 10, 11, 12]
+    assert fl[0, 0, 412].item() == 8 / 0.05 and fl[0, 4, 412].item() == 16 / 0.05
+    assert fl[0, 1, 409].item() == 1.5 * 8 and fl[0, 2, 410].item() == 1.5 * 8
+    assert abs(scores[0, 0, 0].item() - 0.5) < 1e-7
+    assert torch.allclose(boxes[0, 0], torch.tensor([0.5 - 8, 0.5 - 8, 0.5 + 8, 0.5 + 8]) * 8)
