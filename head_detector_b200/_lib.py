@@ -67,6 +67,8 @@ _SIGS = {
     "vgh_detector_run_device": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_void_p]),
     "vgh_detector_set_override": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "vgh_detector_profile": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "vgh_detector_autotune": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "vgh_detector_op_config": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "vgh_detector_launch_count": (C.c_int, [C.c_void_p]),
 }
 EXPORTS = tuple(_SIGS)

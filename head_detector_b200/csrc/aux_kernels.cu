@@ -14,80 +14,83 @@ namespace vgh {
 // ---------------------------------------------------------------------------------------- stem
 // 3x3 stride-2 pad-1 conv, 3 -> 48 channels, ReLU; input uint8 NHWC (the /255 of detector.py:51 is
 // folded into the fp32 weights), output bf16 NHWC with 64 channels (48 real + 16 zeros so that the
-// next layer's K blocks are 64 wide).  thread = (pixel, 16-channel group).
-__global__ void __launch_bounds__(256) stem_conv_kernel(const uint8_t* __restrict__ img, const float* __restrict__ w,
+// next layer's K blocks are 64 wide).  thread = one output pixel, all 48 channels in 3 passes of 16.
+__global__ void __launch_bounds__(128) stem_conv_kernel(const uint8_t* __restrict__ img, const float* __restrict__ w,
                                                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
                                                         int B, int S) {
-  __shared__ float ws[48 * 27];
-  __shared__ float bs[48];
-  for (int i = threadIdx.x; i < 48 * 27; i += blockDim.x) ws[i] = w[i];
+  // weights transposed to [tap][48] so that 4 output channels come from one broadcast 128-bit load
+  __shared__ __align__(16) float ws[27 * 48];
+  __shared__ __align__(16) float bs[48];
+  for (int i = threadIdx.x; i < 48 * 27; i += blockDim.x) {
+    const int co = i / 27, t = i - co * 27;
+    ws[t * 48 + co] = w[i];
+  }
   for (int i = threadIdx.x; i < 48; i += blockDim.x) bs[i] = bias[i];
   __syncthreads();
   const int Ho = S >> 1;
-  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  // a warp handles 32 consecutive output pixels of one row-major stream, one channel group
   const long long total_pix = static_cast<long long>(B) * Ho * Ho;
-  const long long pix_blocks = (total_pix + 31) / 32;
-  const long long pb = warp_global >> 2;
-  const int grp = warp_global & 3;
-  if (pb >= pix_blocks) return;
-  const long long pix = pb * 32 + lane;
+  const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (pix >= total_pix) return;
   const int ow = static_cast<int>(pix % Ho);
   const int oh = static_cast<int>((pix / Ho) % Ho);
   const int b = static_cast<int>(pix / (static_cast<long long>(Ho) * Ho));
-  uint4* op = reinterpret_cast<uint4*>(out + pix * 64 + grp * 16);
-  if (grp == 3) {
-    op[0] = make_uint4(0, 0, 0, 0);
-    op[1] = make_uint4(0, 0, 0, 0);
-    return;
-  }
   float x[27];
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
     const int ih = 2 * oh + ky - 1;
+    const bool row_ok = ih >= 0 && ih < S;
+    const uint8_t* rowp = img + (static_cast<size_t>(b) * S + (row_ok ? ih : 0)) * S * 3;
 #pragma unroll
     for (int kx = 0; kx < 3; ++kx) {
       const int iw = 2 * ow + kx - 1;
-      const bool ok = ih >= 0 && ih < S && iw >= 0 && iw < S;
-      const uint8_t* p = img + ((static_cast<size_t>(b) * S + (ok ? ih : 0)) * S + (ok ? iw : 0)) * 3;
+      const bool ok = row_ok && iw >= 0 && iw < S;
+      const uint8_t* p = rowp + (ok ? iw : 0) * 3;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) x[(ky * 3 + kx) * 3 + c] = ok ? static_cast<float>(p[c]) : 0.f;
+      for (int c = 0; c < 3; ++c) x[(ky * 3 + kx) * 3 + c] = ok ? static_cast<float>(__ldg(p + c)) : 0.f;
     }
   }
-  uint32_t packed[8];
+  uint4* op = reinterpret_cast<uint4*>(out + pix * 64);
+#pragma unroll 1
+  for (int g = 0; g < 3; ++g) {  // 16 output channels per pass
+    float acc[16];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float r[2];
+    for (int j = 0; j < 16; ++j) acc[j] = bs[g * 16 + j];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int co = grp * 16 + j * 2 + q;
-      float acc = bs[co];
+    for (int t = 0; t < 27; ++t) {
+      const float4* wp = reinterpret_cast<const float4*>(ws + t * 48 + g * 16);
 #pragma unroll
-      for (int t = 0; t < 27; ++t) acc = fmaf(ws[co * 27 + t], x[t], acc);
-      r[q] = fmaxf(acc, 0.f);
+      for (int q = 0; q < 4; ++q) {
+        const float4 w4 = wp[q];
+        acc[4 * q] = fmaf(w4.x, x[t], acc[4 * q]);
+        acc[4 * q + 1] = fmaf(w4.y, x[t], acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(w4.z, x[t], acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(w4.w, x[t], acc[4 * q + 3]);
+      }
     }
-    __nv_bfloat162 h = __floats2bfloat162_rn(r[0], r[1]);
-    packed[j] = *reinterpret_cast<uint32_t*>(&h);
+    uint32_t packed[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(acc[2 * j], 0.f), fmaxf(acc[2 * j + 1], 0.f));
+      packed[j] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    op[2 * g] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    op[2 * g + 1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
   }
-  op[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-  op[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+  op[6] = make_uint4(0, 0, 0, 0);  // channels 48..63: zero padding (next layer's K blocks are 64 wide)
+  op[7] = make_uint4(0, 0, 0, 0);
 }
 
 int stem_conv_launch(const uint8_t* img, const float* w, const float* bias, __nv_bfloat16* out, int B, int S,
                      cudaStream_t stream) {
   const long long Ho = S / 2;
-  const long long pix_blocks = (static_cast<long long>(B) * Ho * Ho + 31) / 32;
-  const long long warps = pix_blocks * 4;
-  const int blocks = static_cast<int>((warps * 32 + 255) / 256);
-  stem_conv_kernel<<<blocks, 256, 0, stream>>>(img, w, bias, out, B, S);
+  const long long total = static_cast<long long>(B) * Ho * Ho;
+  stem_conv_kernel<<<static_cast<int>((total + 127) / 128), 128, 0, stream>>>(img, w, bias, out, B, S);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
 // ---------------------------------------------------------------------------------------- SPP
 // max-pool k=5,9,13 stride 1 (pad k/2 with -inf) of channel slice [0,C) of a [B,H,W,4C] buffer into
-// slices 1,2,3.  thread = (pixel, 8 channels); nested windows share the loads.
+// slices 1,2,3.
 __device__ __forceinline__ void max8(uint4& m, const uint4 v) {
   __nv_bfloat162* a = reinterpret_cast<__nv_bfloat162*>(&m);
   const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&v);
@@ -95,41 +98,64 @@ __device__ __forceinline__ void max8(uint4& m, const uint4 v) {
   for (int i = 0; i < 4; ++i) a[i] = __hmax2(a[i], b[i]);
 }
 
-__global__ void __launch_bounds__(256) spp_pool_kernel(__nv_bfloat16* __restrict__ buf, int B, int H, int W, int C) {
-  const int c8n = C / 8;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = static_cast<long long>(B) * H * W * c8n;
-  if (idx >= total) return;
-  const int c8 = static_cast<int>(idx % c8n);
-  const long long pix = idx / c8n;
-  const int w = static_cast<int>(pix % W);
-  const int h = static_cast<int>((pix / W) % H);
-  const int b = static_cast<int>(pix / (static_cast<long long>(W) * H));
-  const int CT = 4 * C;
-  const uint32_t ninf2 = 0xFF80FF80u;  // bf16 -inf pair
-  uint4 m5 = make_uint4(ninf2, ninf2, ninf2, ninf2), m9 = m5, m13 = m5;
-  for (int dy = -6; dy <= 6; ++dy) {
-    const int y = h + dy;
-    if (y < 0 || y >= H) continue;
-    for (int dx = -6; dx <= 6; ++dx) {
-      const int x = w + dx;
-      if (x < 0 || x >= W) continue;
-      const uint4 v = *reinterpret_cast<const uint4*>(buf + ((static_cast<size_t>(b) * H + y) * W + x) * CT + c8 * 8);
-      const int r = max(abs(dy), abs(dx));
-      max8(m13, v);
-      if (r <= 4) max8(m9, v);
-      if (r <= 2) max8(m5, v);
+// CTA = one image x CH channels; the H x W x CH slab lives in shared memory and the three pools are
+// computed as cascaded separable 5-wide maxima (mp9 = mp5(mp5), mp13 = mp5(mp9); -inf padding).
+template <bool kRows>
+__device__ __forceinline__ void max5_pass(const uint4* __restrict__ src, uint4* __restrict__ dst, int H, int W, int L) {
+  for (int i = threadIdx.x; i < H * W * L; i += blockDim.x) {
+    const int l = i % L, pix = i / L;
+    const int x = pix % W, y = pix / W;
+    uint4 m = src[i];
+#pragma unroll
+    for (int d = -2; d <= 2; ++d) {
+      if (d == 0) continue;
+      const int xx = kRows ? x + d : x, yy = kRows ? y : y + d;
+      if (xx < 0 || xx >= W || yy < 0 || yy >= H) continue;
+      max8(m, src[(yy * W + xx) * L + l]);
     }
+    dst[i] = m;
   }
-  __nv_bfloat16* o = buf + static_cast<size_t>(pix) * CT + c8 * 8;
-  *reinterpret_cast<uint4*>(o + C) = m5;
-  *reinterpret_cast<uint4*>(o + 2 * C) = m9;
-  *reinterpret_cast<uint4*>(o + 3 * C) = m13;
+}
+
+__global__ void __launch_bounds__(256) spp_pool_kernel(__nv_bfloat16* __restrict__ buf, int B, int H, int W, int C, int CH) {
+  extern __shared__ __align__(16) uint8_t spp_smem[];
+  const int L = CH / 8;  // uint4 lanes per pixel
+  uint4* b0 = reinterpret_cast<uint4*>(spp_smem);
+  uint4* b1 = b0 + H * W * L;
+  uint4* b2 = b1 + H * W * L;
+  const int chunks = C / CH;
+  const int b = blockIdx.x / chunks, c0 = (blockIdx.x - b * chunks) * CH;
+  const int CT = 4 * C;
+  __nv_bfloat16* base = buf + static_cast<size_t>(b) * H * W * CT + c0;
+  for (int i = threadIdx.x; i < H * W * L; i += blockDim.x)
+    b0[i] = *reinterpret_cast<const uint4*>(base + static_cast<size_t>(i / L) * CT + (i % L) * 8);
+  __syncthreads();
+  uint4* cur = b0;
+  uint4* out = b2;
+  for (int k = 1; k <= 3; ++k) {
+    max5_pass<true>(cur, b1, H, W, L);
+    __syncthreads();
+    max5_pass<false>(b1, out, H, W, L);
+    __syncthreads();
+    for (int i = threadIdx.x; i < H * W * L; i += blockDim.x)
+      *reinterpret_cast<uint4*>(base + static_cast<size_t>(i / L) * CT + k * C + (i % L) * 8) = out[i];
+    uint4* t = cur;
+    cur = out;
+    out = t;
+  }
 }
 
 int spp_pool_launch(__nv_bfloat16* buf, int B, int H, int W, int C, cudaStream_t stream) {
-  const long long total = static_cast<long long>(B) * H * W * (C / 8);
-  spp_pool_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, stream>>>(buf, B, H, W, C);
+  int CH = 32;
+  while (CH > 8 && static_cast<size_t>(H) * W * CH * 2 * 3 > 160 * 1024) CH >>= 1;
+  if (C % CH) return 1;
+  const size_t smem = static_cast<size_t>(H) * W * CH * 2 * 3;
+  static size_t configured = 0;
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(spp_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
+    configured = smem;
+  }
+  spp_pool_kernel<<<B * (C / CH), 256, smem, stream>>>(buf, B, H, W, C, CH);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

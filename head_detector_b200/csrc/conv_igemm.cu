@@ -11,34 +11,43 @@ static thread_local char g_conv_err[256] = "";
 const char* conv_last_error() { return g_conv_err; }
 
 constexpr int kBlockM = 128;
-constexpr int kThreads = 192;  // warp0 TMA, warp1 MMA/TMEM, warps 2..5 epilogue
+constexpr int kEpiWarps = 8;                   // 2 per TMEM lane quarter, each takes every other 16-column chunk
+constexpr int kThreads = 64 + 32 * kEpiWarps;  // warp0 TMA, warp1 MMA/TMEM, warps 2..9 epilogue
 
+// Persistent, warp-specialised implicit-GEMM conv.  Each CTA (one per SM) walks work items
+// item = blockIdx.x + i*gridDim.x, item -> (M group of `mt` 128-pixel tiles, N tile).  The shared-memory
+// ring (TMA -> MMA) runs continuously across items; accumulators are double-buffered in TMEM when
+// 2*mt*block_n <= 512 columns so the epilogue of item i overlaps the main loop of item i+1.
 template <int BK>
 __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvLaunch p) {
   constexpr uint32_t kRowBytes = BK * 2;            // bytes of one K-slab row == swizzle span
-  constexpr uint32_t kABytes = kBlockM * kRowBytes;  // A stage
+  constexpr uint32_t kABytes = kBlockM * kRowBytes;  // one 128-pixel A tile
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_bytes = static_cast<uint32_t>(p.block_n) * kRowBytes;
+  const uint32_t a_stage_bytes = static_cast<uint32_t>(p.mt) * kABytes;  // mt A tiles per stage
   const uint32_t a_base = smem_base;
-  const uint32_t b_base = a_base + p.stages * kABytes;
+  const uint32_t b_base = a_base + p.stages * a_stage_bytes;
   const uint32_t bar_base = b_base + p.stages * b_bytes;  // 8-byte aligned (multiples of 1024)
   const uint32_t full_bar = bar_base;                     // [stages]
   const uint32_t empty_bar = bar_base + 8 * p.stages;     // [stages]
-  const uint32_t tmem_full_bar = bar_base + 16 * p.stages;
-  const uint32_t tmem_slot = tmem_full_bar + 8;
+  const uint32_t tmem_full_bar = bar_base + 16 * p.stages;  // [2]
+  const uint32_t tmem_empty_bar = tmem_full_bar + 16;       // [2]
+  const uint32_t tmem_slot = tmem_empty_bar + 16;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // ---- tile coordinates
   const int tiles_per_img = p.tiles_x * p.tiles_y;
-  const int b_img = blockIdx.x / tiles_per_img;
-  const int t_in = blockIdx.x - b_img * tiles_per_img;
-  const int tyi = t_in / p.tiles_x;
-  const int h0 = tyi * p.th;
-  const int w0 = (t_in - tyi * p.tiles_x) * p.tw;
-  const int n0 = blockIdx.y * p.block_n;
+  const int total_tiles = tiles_per_img * p.B;
+  auto tile_coords = [&](int t, int& b_img, int& h0, int& w0) {
+    t = min(t, total_tiles - 1);  // tail of the last M group: reload the last tile, its epilogue is skipped
+    b_img = t / tiles_per_img;
+    const int t_in = t - b_img * tiles_per_img;
+    const int tyi = t_in / p.tiles_x;
+    h0 = tyi * p.th;
+    w0 = (t_in - tyi * p.tiles_x) * p.tw;
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
@@ -47,7 +56,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       mbar_init(full_bar + 8 * s, 1);
       mbar_init(empty_bar + 8 * s, 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar + 8 * a, 1);
+      mbar_init(tmem_empty_bar + 8 * a, kEpiWarps);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -62,30 +74,38 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
 
   const int cblks = p.cin / BK;
   const int num_kb = p.ntaps * cblks;
+  const uint32_t acc_cols = static_cast<uint32_t>(p.mt * p.block_n);  // TMEM columns of one accumulator stage
 
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
-      const uint32_t tx_bytes = static_cast<uint32_t>(p.tw * p.th) * kRowBytes + b_bytes;
+      const uint32_t tx_bytes = static_cast<uint32_t>(p.mt) * static_cast<uint32_t>(p.tw * p.th) * kRowBytes + b_bytes;
       int stage = 0;
       uint32_t phase = 0;
-      int tap = 0, cb = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-        const uint32_t fb = full_bar + 8 * stage;
-        mbar_arrive_expect_tx(fb, tx_bytes);
-        const int ty = tap / p.kw;
-        const int tx = tap - ty * p.kw;
-        tma_load_4d(a_base + stage * kABytes, &p.tmA, fb, p.cin_off + cb * BK, w0 * p.stride + tx - p.pad,
-                    h0 * p.stride + ty - p.pad, b_img);
-        tma_load_2d(b_base + stage * b_bytes, &p.tmB, fb, tap * p.cin + cb * BK, n0);
-        if (++cb == cblks) {
-          cb = 0;
-          ++tap;
-        }
-        if (++stage == p.stages) {
-          stage = 0;
-          phase ^= 1;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        const int mg = item / p.n_tiles;
+        const int n0 = (item - mg * p.n_tiles) * p.block_n;
+        int tb[4], th0[4], tw0[4];
+        for (int i = 0; i < p.mt; ++i) tile_coords(mg * p.mt + i, tb[i], th0[i], tw0[i]);
+        int tap = 0, cb = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+          const uint32_t fb = full_bar + 8 * stage;
+          mbar_arrive_expect_tx(fb, tx_bytes);
+          const int ty = tap / p.kw;
+          const int tx = tap - ty * p.kw;
+          for (int i = 0; i < p.mt; ++i)
+            tma_load_4d(a_base + stage * a_stage_bytes + i * kABytes, &p.tmA, fb, p.cin_off + cb * BK,
+                        tw0[i] * p.stride + tx - p.pad, th0[i] * p.stride + ty - p.pad, tb[i]);
+          tma_load_2d(b_base + stage * b_bytes, &p.tmB, fb, tap * p.cin + cb * BK, n0);
+          if (++cb == cblks) {
+            cb = 0;
+            ++tap;
+          }
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     }
@@ -95,87 +115,141 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       const uint32_t idesc = umma_idesc_bf16(kBlockM, static_cast<uint32_t>(p.block_n));
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(full_bar + 8 * stage, phase);
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        mbar_wait(tmem_empty_bar + 8 * acc, acc_phase ^ 1);  // epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint64_t a_desc = umma_smem_desc(a_base + stage * kABytes, kRowBytes);
-        const uint64_t b_desc = umma_smem_desc(b_base + stage * b_bytes, kRowBytes);
+        const uint32_t d_base = tmem_acc + acc * acc_cols;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar + 8 * stage, phase);
+          tc_fence_after();
+          const uint64_t b_desc = umma_smem_desc(b_base + stage * b_bytes, kRowBytes);
+          for (int i = 0; i < p.mt; ++i) {
+            const uint64_t a_desc = umma_smem_desc(a_base + stage * a_stage_bytes + i * kABytes, kRowBytes);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // advance 16 elements (32 B) along K inside the swizzle span: +2 in 16-byte units
-          umma_bf16(tmem_acc, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              // advance 16 elements (32 B) along K inside the swizzle span: +2 in 16-byte units
+              umma_bf16(d_base + i * p.block_n, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(empty_bar + 8 * stage);  // frees the smem slot once these MMAs retire
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
-        umma_commit(empty_bar + 8 * stage);  // frees the smem slot once these MMAs retire
-        if (++stage == p.stages) {
-          stage = 0;
-          phase ^= 1;
+        umma_commit(tmem_full_bar + 8 * acc);  // accumulators of this item complete
+        if (++acc == p.acc_stages) {
+          acc = 0;
+          acc_phase ^= 1;
         }
       }
-      umma_commit(tmem_full_bar);  // accumulator complete
     }
   } else {
     // ===================== epilogue: TMEM -> registers -> global =====================
-    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
+    const int ew = warp - 2;
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are the ones this warp may read
+    const int chunk0 = ew >> 2;    // two warps share a quarter: even / odd 16-column chunks
     const int r = quarter * 32 + lane;
     const int ly = r / p.tw;
     const int lx = r - ly * p.tw;
-    const int oh = h0 + ly, ow = w0 + lx;
-    const bool row_ok = (r < p.tw * p.th) && (oh < p.Ho) && (ow < p.Wo);
-
-    int n_shift = 0;  // channel shift when the n-tile addresses a sub-pixel of the 2x2 transpose conv
-    int ph = oh, pw = ow;
-    if (p.up) {
-      const int sub = n0 / p.up_cout;
-      n_shift = sub * p.up_cout;
-      ph = 2 * oh + (sub >> 1);
-      pw = 2 * ow + (sub & 1);
-    }
-    const size_t out_pix = (static_cast<size_t>(b_img) * p.out_H + ph) * p.out_W + pw;
-    const size_t out_off = out_pix * p.out_cstride + p.out_coff + (n0 - n_shift);
-    const size_t res_off =
-        ((static_cast<size_t>(b_img) * p.Ho + oh) * p.Wo + ow) * p.res_cstride + p.res_coff + n0;
-
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
     const int n_chunks = p.block_n >> 4;
-    for (int c = 0; c < n_chunks; ++c) {
-      uint32_t v[16];
-      tmem_ld16(taddr + c * 16, v);
-      tmem_ld_wait();
-      const int n = n0 + c * 16;
-      if (!row_ok || n >= p.n_total) continue;
-      float f[16];
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const int mg = item / p.n_tiles;
+      const int n0 = (item - mg * p.n_tiles) * p.block_n;
+      mbar_wait(tmem_full_bar + 8 * acc, acc_phase);
+      tc_fence_after();
+      for (int ti = 0; ti < p.mt; ++ti) {
+        const int tile = mg * p.mt + ti;
+        if (tile >= total_tiles) break;
+        int b_img, h0, w0;
+        tile_coords(tile, b_img, h0, w0);
+        const int oh = h0 + ly, ow = w0 + lx;
+        const bool row_ok = (r < p.tw * p.th) && (oh < p.Ho) && (ow < p.Wo);
+        int n_shift = 0;  // channel shift when the n-tile addresses a sub-pixel of the 2x2 transpose conv
+        int ph = oh, pw = ow;
+        if (p.up) {
+          const int sub = n0 / p.up_cout;
+          n_shift = sub * p.up_cout;
+          ph = 2 * oh + (sub >> 1);
+          pw = 2 * ow + (sub & 1);
+        }
+        const size_t out_pix = (static_cast<size_t>(b_img) * p.out_H + ph) * p.out_W + pw;
+        const size_t out_off = out_pix * p.out_cstride + p.out_coff + (n0 - n_shift);
+        const size_t res_off =
+            ((static_cast<size_t>(b_img) * p.Ho + oh) * p.Wo + ow) * p.res_cstride + p.res_coff + n0;
+        const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + acc * acc_cols + ti * p.block_n;
+        const bool use_res = (p.res != nullptr) && row_ok;
+        uint4 rq0 = make_uint4(0, 0, 0, 0), rq1 = rq0, nq0 = rq0, nq1 = rq0;
+        if (use_res && chunk0 < n_chunks && n0 + chunk0 * 16 < p.n_total) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.res + res_off + chunk0 * 16);
+          rq0 = __ldg(rp);
+          rq1 = __ldg(rp + 1);
+        }
+        for (int c = chunk0; c < n_chunks; c += 2) {
+          const int n = n0 + c * 16;
+          if (use_res && c + 2 < n_chunks && n + 32 < p.n_total) {  // prefetch the next chunk's residual
+            const uint4* rp = reinterpret_cast<const uint4*>(p.res + res_off + (c + 2) * 16);
+            nq0 = __ldg(rp);
+            nq1 = __ldg(rp + 1);
+          }
+          uint32_t v[16];
+          tmem_ld16(taddr + c * 16, v);
+          tmem_ld_wait();
+          if (row_ok && n < p.n_total) {
+            float f[16];
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float x = __uint_as_float(v[i]) + __ldg(p.bias + n + i);
-        f[i] = p.relu ? fmaxf(x, 0.f) : x;
-      }
-      if (p.res != nullptr) {
-        const uint4* rp = reinterpret_cast<const uint4*>(p.res + res_off + c * 16);
-        uint4 q0 = __ldg(rp), q1 = __ldg(rp + 1);
-        const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+            for (int i = 0; i < 4; ++i) {
+              const float4 b4 = __ldg(bp + i);
+              f[4 * i] = __uint_as_float(v[4 * i]) + b4.x;
+              f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4.y;
+              f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4.z;
+              f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4.w;
+            }
+            if (p.relu) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
-          f[2 * i] = fmaf(p.res_alpha, __bfloat162float(h.x), f[2 * i]);
-          f[2 * i + 1] = fmaf(p.res_alpha, __bfloat162float(h.y), f[2 * i + 1]);
+              for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+            }
+            if (p.res != nullptr) {
+              const uint32_t w[8] = {rq0.x, rq0.y, rq0.z, rq0.w, rq1.x, rq1.y, rq1.z, rq1.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+                f[2 * i] = fmaf(p.res_alpha, __bfloat162float(h.x), f[2 * i]);
+                f[2 * i + 1] = fmaf(p.res_alpha, __bfloat162float(h.y), f[2 * i + 1]);
+              }
+            }
+            if (p.out_fp32) {
+              float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + out_off + c * 16);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+            } else {
+              uint32_t w[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+                w[i] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + out_off + c * 16);
+              op[0] = make_uint4(w[0], w[1], w[2], w[3]);
+              op[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            }
+          }
+          rq0 = nq0;
+          rq1 = nq1;
         }
       }
-      if (p.out_fp32) {
-        float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + out_off + c * 16);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-      } else {
-        uint32_t w[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-          w[i] = *reinterpret_cast<uint32_t*>(&h);
-        }
-        uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + out_off + c * 16);
-        op[0] = make_uint4(w[0], w[1], w[2], w[3]);
-        op[1] = make_uint4(w[4], w[5], w[6], w[7]);
+      // this warp is done reading the accumulator stage: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty_bar + 8 * acc);
+      if (++acc == p.acc_stages) {
+        acc = 0;
+        acc_phase ^= 1;
       }
     }
   }
@@ -207,16 +281,48 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int conv_pick_stages(int block_n, int bk) {
-  const int stage = (kBlockM + block_n) * bk * 2;
-  int s = (104 * 1024) / stage;  // two CTAs per SM: the second CTA's main loop hides this one's epilogue
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0, n = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    g_num_sms = n;
+  }
+  return g_num_sms;
+}
+
+int conv_default_mt(int block_n) {
+  // M tiles per CTA sharing one weight stream, such that two accumulator stages still fit in the
+  // 512 TMEM columns (epilogue/main-loop overlap): N<=64 -> 4, N<=128 -> 2, else 1
+  int mt = 256 / block_n;
+  if (mt > 4) mt = 4;
+  if (mt < 1) mt = 1;
+  if (mt == 3) mt = 2;
+  return mt;
+}
+
+int conv_pick_stages(int block_n, int bk, int mt) {
+  const int stage = (kBlockM * mt + block_n) * bk * 2;
+  int s = (200 * 1024) / stage;  // one persistent CTA per SM owns the shared memory
   if (s < 2) s = 2;
   if (s > 8) s = 8;
   return s;
 }
 
 size_t conv_smem_bytes(const ConvLaunch& L, int bk) {
-  return 1024 + static_cast<size_t>(L.stages) * (kBlockM + L.block_n) * bk * 2 + 16 * L.stages + 16;
+  return 1024 + static_cast<size_t>(L.stages) * (kBlockM * L.mt + L.block_n) * bk * 2 + 16 * L.stages + 64;
+}
+
+// fills the derived scheduling fields (call after tiles / block_n / mt are set)
+void conv_finalize(ConvLaunch& L) {
+  L.n_tiles = (L.n_total + L.block_n - 1) / L.block_n;
+  const int m_groups = (L.tiles_x * L.tiles_y * L.B + L.mt - 1) / L.mt;
+  L.num_items = m_groups * L.n_tiles;
+  L.acc_stages = (2 * L.mt * L.block_n <= 512) ? 2 : 1;
+  int cols = 32;
+  while (cols < L.acc_stages * L.mt * L.block_n) cols <<= 1;
+  L.tmem_cols = cols;
 }
 
 int conv_make_tensor_maps(ConvLaunch& L, const void* in_base, int in_C, int in_H, int in_W, const void* w_base,
@@ -267,7 +373,7 @@ static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
     }
     configured = smem;
   }
-  dim3 grid(L.tiles_x * L.tiles_y * L.B, (L.n_total + L.block_n - 1) / L.block_n);
+  dim3 grid(L.num_items < num_sms() ? L.num_items : num_sms());
   conv_igemm_kernel<BK><<<grid, kThreads, smem, stream>>>(L);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

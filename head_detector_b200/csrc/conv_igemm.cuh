@@ -35,6 +35,8 @@ struct ConvLaunch {
   int res_cstride, res_coff;
   float res_alpha;
   int stages, tmem_cols;
+  int mt;                        // M tiles (128-pixel accumulators) per work item sharing one weight stream
+  int acc_stages, n_tiles, num_items;  // TMEM accumulator stages (1|2), N tiles, work items (persistent CTAs)
 };
 
 // Host side (conv_igemm.cu)
@@ -42,7 +44,9 @@ int conv_make_tensor_maps(ConvLaunch& L, const void* in_base, int in_C, int in_H
                           int k_total, int n_pad, int bk);
 int conv_launch(const ConvLaunch& L, int bk, cudaStream_t stream);
 size_t conv_smem_bytes(const ConvLaunch& L, int bk);
-int conv_pick_stages(int block_n, int bk);
+int conv_pick_stages(int block_n, int bk, int mt);
+int conv_default_mt(int block_n);
+void conv_finalize(ConvLaunch& L);
 const char* conv_last_error();
 
 }  // namespace vgh

@@ -78,6 +78,7 @@ struct OpRt {
   vgh_op_desc d;
   ConvLaunch L;
   int bk;
+  int cfg_mt = 0, cfg_stages = 0, cfg_tw = 0, cfg_th = 0;  // 0 = heuristic; set by vgh_detector_autotune
 };
 
 struct vgh_detector {
@@ -98,6 +99,7 @@ struct vgh_detector {
   float *params = nullptr, *head_xform = nullptr, *verts = nullptr, *rot = nullptr, *img_xform = nullptr;
   const float *ovr_boxes = nullptr, *ovr_scores = nullptr;
   cudaGraphExec_t graph = nullptr;
+  cudaStream_t cap_stream = nullptr;  // capture needs a non-legacy stream; the graph then replays anywhere
   float g_conf = -1.f, g_iou = -1.f;
   int g_topk = -1;
   int launches = 0;
@@ -139,7 +141,7 @@ static int build_conv(vgh_detector* d, OpRt& o) {
   L.stride = q.stride;
   L.Ho = q.up ? ib.H : (ib.H + q.stride - 1) / q.stride;
   L.Wo = q.up ? ib.W : (ib.W + q.stride - 1) / q.stride;
-  pick_tile(L.Ho, L.Wo, L.tw, L.th);
+  if (o.cfg_tw > 0) { L.tw = o.cfg_tw; L.th = o.cfg_th; } else pick_tile(L.Ho, L.Wo, L.tw, L.th);
   L.tiles_x = (L.Wo + L.tw - 1) / L.tw;
   L.tiles_y = (L.Ho + L.th - 1) / L.th;
   L.cin_off = q.in_coff;
@@ -175,10 +177,10 @@ static int build_conv(vgh_detector* d, OpRt& o) {
     L.res_coff = q.res_coff;
     L.res_alpha = q.res_alpha;
   }
-  L.stages = conv_pick_stages(L.block_n, o.bk);
-  int cols = 32;
-  while (cols < L.block_n) cols <<= 1;
-  L.tmem_cols = cols;
+  L.mt = o.cfg_mt > 0 ? o.cfg_mt : conv_default_mt(L.block_n);
+  L.stages = o.cfg_stages > 0 ? o.cfg_stages : conv_pick_stages(L.block_n, o.bk, L.mt);
+  if (L.mt * L.block_n > 512) return fail(2, "mt %d x block_n %d exceeds TMEM", L.mt, L.block_n);
+  conv_finalize(L);
   if (ib.fp32) return fail(2, "conv input must be bf16");
   int rc = conv_make_tensor_maps(L, d->buf_ptr[q.in_buf], ib.C, ib.H, ib.W, d->weights + q.w_off, q.k_total, q.n_pad,
                                  o.bk);
@@ -189,6 +191,7 @@ static int build_conv(vgh_detector* d, OpRt& o) {
 extern "C" void vgh_detector_destroy(vgh_detector* d) {
   if (!d) return;
   if (d->graph) cudaGraphExecDestroy(d->graph);
+  if (d->cap_stream) cudaStreamDestroy(d->cap_stream);
   for (void* p : d->buf_ptr) cudaFree(p);
   void* ptrs[] = {d->weights, d->bias, d->stem_w, d->stem_b, d->input, d->boxes, d->scores, d->keep_boxes,
                   d->keep_scores, d->keep_idx, d->keep_cnt, d->offsets, d->head_img, d->params, d->head_xform,
@@ -331,6 +334,63 @@ static int run_post(vgh_detector* d, float conf, float iou, int top_k, const flo
   return 0;
 }
 
+// Per-op configuration search on the device: every conv op is timed under a few (mt, stages)
+// candidates (inputs are whatever the buffers hold - timing does not depend on values) and the
+// fastest is kept.  Invalidates the captured graph.
+extern "C" int vgh_detector_autotune(vgh_detector* d, int iters, void* stream) {
+  if (!d) return fail(1, "null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (d->graph) { cudaGraphExecDestroy(d->graph); d->graph = nullptr; }
+  cudaEvent_t e0, e1;
+  CUDA_OK(cudaEventCreate(&e0));
+  CUDA_OK(cudaEventCreate(&e1));
+  if (iters < 1) iters = 3;
+  for (OpRt& o : d->ops) {
+    if (o.d.kind != VGH_OP_CONV) continue;
+    float best = 1e30f;
+    int best_mt = 0, best_st = 0;
+    const int bn = o.L.block_n;
+    for (int mt : {1, 2, 4}) {
+      if (mt * bn > 512) continue;
+      for (int variant = 0; variant < 2; ++variant) {
+        OpRt t = o;
+        t.cfg_mt = mt;
+        const int stage_bytes = (128 * mt + bn) * t.bk * 2;
+        int st = (variant == 0 ? 200 * 1024 : 100 * 1024) / stage_bytes;  // 1 CTA/SM deep vs 2 CTAs/SM
+        if (st > 8) st = 8;
+        if (st < 2) { if (variant == 1) continue; st = 2; }
+        if ((size_t)st * stage_bytes > 210 * 1024) continue;
+        t.cfg_stages = st;
+        if (build_conv(d, t)) continue;
+        if (conv_launch(t.L, t.bk, s)) continue;  // warm-up (also sets the smem attribute)
+        cudaEventRecord(e0, s);
+        for (int i = 0; i < iters; ++i) conv_launch(t.L, t.bk, s);
+        cudaEventRecord(e1, s);
+        if (cudaStreamSynchronize(s) != cudaSuccess) return fail(7, "autotune launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) { best = ms; best_mt = mt; best_st = st; }
+      }
+    }
+    if (best_mt) {
+      o.cfg_mt = best_mt;
+      o.cfg_stages = best_st;
+      int rc = build_conv(d, o);
+      if (rc) return rc;
+    }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return 0;
+}
+// Reports the configuration of conv op i: out[0..5] = mt, stages, block_n, bk, tw, th.
+extern "C" int vgh_detector_op_config(const vgh_detector* d, int op, int32_t* out6) {
+  if (!d || op < 0 || op >= (int)d->ops.size() || !out6) return fail(1, "bad argument");
+  const OpRt& o = d->ops[op];
+  out6[0] = o.L.mt; out6[1] = o.L.stages; out6[2] = o.L.block_n; out6[3] = o.bk; out6[4] = o.L.tw; out6[5] = o.L.th;
+  return 0;
+}
+
 // Eager execution with one CUDA-event pair around every plan op and every post-processing stage.
 extern "C" int vgh_detector_profile(vgh_detector* d, int iters, float conf_thr, float iou_thr, int top_k,
                                     float* ms_out, int capacity, void* stream) {
@@ -434,9 +494,12 @@ extern "C" int vgh_detector_set_override(vgh_detector* d, const float* boxes_dev
   return 0;
 }
 
-static int ensure_graph(vgh_detector* d, float conf, float iou, int top_k, cudaStream_t s) {
+static int ensure_graph(vgh_detector* d, float conf, float iou, int top_k, cudaStream_t user) {
   if (d->graph && d->g_conf == conf && d->g_iou == iou && d->g_topk == top_k) return 0;
   if (d->graph) { cudaGraphExecDestroy(d->graph); d->graph = nullptr; }
+  if (!d->cap_stream) CUDA_OK(cudaStreamCreateWithFlags(&d->cap_stream, cudaStreamNonBlocking));
+  cudaStream_t s = d->cap_stream;
+  CUDA_OK(cudaStreamSynchronize(user));  // order the (re)build after whatever the caller queued
   // one eager pass first: sets the max-dynamic-smem attributes outside of capture and surfaces errors
   int launches = 0;
   int rc = run_forward(d, d->input, s, &launches);

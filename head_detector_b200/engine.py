@@ -157,6 +157,14 @@ class Engine:
         t = torch.from_numpy(arr) if fp32 else torch.from_numpy(arr.view(np.int16)).view(torch.bfloat16).float()
         return t.reshape(self.B, h, w, c)
 
+    def autotune(self, iters=3):
+        _lib.check(_lib.lib().vgh_detector_autotune(self._h, iters, _lib.stream_ptr()), "autotune")
+
+    def op_config(self, i):
+        out = (C.c_int32 * 6)()
+        _lib.check(_lib.lib().vgh_detector_op_config(self._h, i, out), "op_config")
+        return dict(zip(("mt", "stages", "block_n", "bk", "tw", "th"), out))
+
     def profile(self, iters=5, conf=0.5, iou=0.5, top_k=1000):
         """Per-op device times (ms) over the staging input: list of (label, ms, flops) + post stages."""
         n = len(self.plan.ops) + 4

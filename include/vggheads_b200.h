@@ -156,6 +156,11 @@ int vgh_detector_set_override(vgh_detector* d, const float* boxes_dev, const flo
  * (capacity >= n_ops + 4) = [op_0 .. op_{n-1}, box_decode, select_nms, gather, flame_decode]. */
 int vgh_detector_profile(vgh_detector* d, int iters, float conf_thr, float iou_thr, int top_k, float* ms_out,
                          int capacity, void* stream);
+/* Device-side configuration search: times every conv op under a few (M-tiles per CTA, pipeline
+ * depth) candidates and keeps the fastest.  Optional; call once after create. */
+int vgh_detector_autotune(vgh_detector* d, int iters, void* stream);
+/* Configuration of plan op `op`: out6 = {m_tiles_per_cta, stages, block_n, block_k, tile_w, tile_h}. */
+int vgh_detector_op_config(const vgh_detector* d, int op, int32_t* out6);
 /* Number of kernel launches one forward+postprocess issues (graph nodes), for reporting. */
 int vgh_detector_launch_count(const vgh_detector* d);
 
