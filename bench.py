@@ -178,6 +178,7 @@ def run_ours(args, rank, world, local_rank):
     dev_imgs = [h.cuda() for h in host_imgs]
     boxes, scores = synth.engineered_heads(B, eng.A, IMAGE_SIZE, HEADS_PER_IMAGE, seed=7 + rank)
     eng.set_override(boxes.cuda(), scores.cuda())
+    eng.autotune(3)  # one-off per-layer kernel configuration search (setup, not timed)
     out = eng.alloc_host_outputs(B * 100)
     stream = torch.cuda.current_stream()
 

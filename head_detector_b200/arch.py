@@ -235,6 +235,8 @@ def pack(plan: Plan, w: Dict[str, torch.Tensor]) -> PackedNet:
         cin, taps = op.src[2], op.k * op.k
         block_n = _auto_block_n(op.cout, op.up, op.up_cout)
         n_pad = (op.cout + block_n - 1) // block_n * block_n
+        if op.cout <= 128 and not op.up and not plan.bufs[op.dst[0]][3]:
+            n_pad = 128  # eligible for the operand-swapped kernel (M = 128 weight rows, zero padded)
         M = torch.zeros(n_pad, taps, cin, dtype=torch.float32)
         bvec = torch.zeros(n_pad, dtype=torch.float32)
         for p in op.parts:

@@ -183,23 +183,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
             ((static_cast<size_t>(b_img) * p.Ho + oh) * p.Wo + ow) * p.res_cstride + p.res_coff + n0;
         const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + acc * acc_cols + ti * p.block_n;
         const bool use_res = (p.res != nullptr) && row_ok;
-        uint4 rq0 = make_uint4(0, 0, 0, 0), rq1 = rq0, nq0 = rq0, nq1 = rq0;
-        if (use_res && chunk0 < n_chunks && n0 + chunk0 * 16 < p.n_total) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.res + res_off + chunk0 * 16);
-          rq0 = __ldg(rp);
-          rq1 = __ldg(rp + 1);
-        }
-        for (int c = chunk0; c < n_chunks; c += 2) {
-          const int n = n0 + c * 16;
-          if (use_res && c + 2 < n_chunks && n + 32 < p.n_total) {  // prefetch the next chunk's residual
-            const uint4* rp = reinterpret_cast<const uint4*>(p.res + res_off + (c + 2) * 16);
-            nq0 = __ldg(rp);
-            nq1 = __ldg(rp + 1);
+        // chunks of this warp: chunk0, chunk0+2, ...; handled four at a time so that the residual
+        // loads of a whole group are in flight before the first one is consumed
+        for (int cg = chunk0; cg < n_chunks; cg += 8) {
+          uint4 rq[4][2];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int c = cg + 2 * g;
+            rq[g][0] = make_uint4(0, 0, 0, 0);
+            rq[g][1] = rq[g][0];
+            if (use_res && c < n_chunks && n0 + c * 16 < p.n_total) {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.res + res_off + c * 16);
+              rq[g][0] = __ldg(rp);
+              rq[g][1] = __ldg(rp + 1);
+            }
           }
-          uint32_t v[16];
-          tmem_ld16(taddr + c * 16, v);
-          tmem_ld_wait();
-          if (row_ok && n < p.n_total) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int c = cg + 2 * g;
+            if (c >= n_chunks) break;
+            const int n = n0 + c * 16;
+            uint32_t v[16];
+            tmem_ld16(taddr + c * 16, v);
+            tmem_ld_wait();
+            if (!(row_ok && n < p.n_total)) continue;
             float f[16];
             const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
@@ -215,7 +222,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
               for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
             }
             if (p.res != nullptr) {
-              const uint32_t w[8] = {rq0.x, rq0.y, rq0.z, rq0.w, rq1.x, rq1.y, rq1.z, rq1.w};
+              const uint32_t w[8] = {rq[g][0].x, rq[g][0].y, rq[g][0].z, rq[g][0].w, rq[g][1].x, rq[g][1].y, rq[g][1].z, rq[g][1].w};
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
@@ -239,8 +246,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
               op[1] = make_uint4(w[4], w[5], w[6], w[7]);
             }
           }
-          rq0 = nq0;
-          rq1 = nq1;
         }
       }
       // this warp is done reading the accumulator stage: hand it back to the MMA warp
@@ -316,6 +321,17 @@ size_t conv_smem_bytes(const ConvLaunch& L, int bk) {
 
 // fills the derived scheduling fields (call after tiles / block_n / mt are set)
 void conv_finalize(ConvLaunch& L) {
+  if (L.swap) {  // one item = one (tw x th)-pixel tile; all (<=128) output channels
+    L.mt = 1;
+    L.n_tiles = 1;
+    L.num_items = L.tiles_x * L.tiles_y * L.B;
+    const int npix = L.tw * L.th;
+    L.acc_stages = (2 * npix <= 512) ? 2 : 1;
+    int cols = 32;
+    while (cols < L.acc_stages * npix) cols <<= 1;
+    L.tmem_cols = cols;
+    return;
+  }
   L.n_tiles = (L.n_total + L.block_n - 1) / L.block_n;
   const int m_groups = (L.tiles_x * L.tiles_y * L.B + L.mt - 1) / L.mt;
   L.num_items = m_groups * L.n_tiles;
@@ -347,7 +363,7 @@ int conv_make_tensor_maps(ConvLaunch& L, const void* in_base, int in_C, int in_H
   {
     cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)n_pad};
     cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
-    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)L.block_n};
+    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)(L.swap ? 128 : L.block_n)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&L.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -356,6 +372,29 @@ int conv_make_tensor_maps(ConvLaunch& L, const void* in_base, int in_C, int in_H
       snprintf(g_conv_err, sizeof(g_conv_err), "encode B map failed: %d (K=%d N=%d box %d,%d)", (int)r, k_total, n_pad,
                bk, L.block_n);
       return 3;
+    }
+  }
+  return 0;
+}
+
+int conv_make_io_maps(ConvLaunch& L, void* out_base, const void* res_base) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return 1;
+  for (int which = 0; which < 2; ++which) {
+    const void* base = which == 0 ? out_base : res_base;
+    if (!base) continue;
+    const int C = which == 0 ? L.out_cstride : L.res_cstride;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)L.Wo, (cuuint64_t)L.Ho, (cuuint64_t)L.B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)L.Wo * C * 2, (cuuint64_t)L.Ho * L.Wo * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)L.n_total, (cuuint32_t)L.tw, (cuuint32_t)L.th, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(which == 0 ? &L.tmOut : &L.tmRes, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      snprintf(g_conv_err, sizeof(g_conv_err), "encode io map %d failed: %d (C=%d W=%d H=%d box %d,%d,%d)", which, (int)r, C,
+               L.Wo, L.Ho, L.n_total, L.tw, L.th);
+      return 2;
     }
   }
   return 0;
@@ -384,6 +423,7 @@ static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
 }
 
 int conv_launch(const ConvLaunch& L, int bk, cudaStream_t stream) {
+  if (L.swap) return conv_swap_launch(L, bk, num_sms(), stream, g_conv_err, sizeof(g_conv_err));
   if (bk == 64) return launch_t<64>(L, stream);
   if (bk == 32) return launch_t<32>(L, stream);
   snprintf(g_conv_err, sizeof(g_conv_err), "unsupported BK %d", bk);

@@ -21,6 +21,8 @@ namespace vgh {
 struct ConvLaunch {
   CUtensorMap tmA;  // input  [C_total, W, H, B] bf16 (innermost first)
   CUtensorMap tmB;  // weights [K_total, N_pad]  bf16
+  CUtensorMap tmOut;  // swapped kernel: output  [C_total, W, H, B] bf16, box [n_total, tw, th, 1] (TMA store)
+  CUtensorMap tmRes;  // swapped kernel: residual [C_total, W, H, B] bf16, same box (TMA load)
   const float* bias;             // [N_pad]
   void* out;                     // output buffer base (bf16 or fp32)
   const __nv_bfloat16* res;      // residual buffer base or nullptr
@@ -36,17 +38,22 @@ struct ConvLaunch {
   float res_alpha;
   int stages, tmem_cols;
   int mt;                        // M tiles (128-pixel accumulators) per work item sharing one weight stream
+  int swap;                      // 1: operands swapped (conv_igemm_swap.cu): M = 128 cout rows, N = tw*th pixels
   int acc_stages, n_tiles, num_items;  // TMEM accumulator stages (1|2), N tiles, work items (persistent CTAs)
 };
 
 // Host side (conv_igemm.cu)
 int conv_make_tensor_maps(ConvLaunch& L, const void* in_base, int in_C, int in_H, int in_W, const void* w_base,
                           int k_total, int n_pad, int bk);
+// swapped kernel only: TMA maps of the output slice and (optional) residual slice
+int conv_make_io_maps(ConvLaunch& L, void* out_base, const void* res_base);
 int conv_launch(const ConvLaunch& L, int bk, cudaStream_t stream);
 size_t conv_smem_bytes(const ConvLaunch& L, int bk);
 int conv_pick_stages(int block_n, int bk, int mt);
 int conv_default_mt(int block_n);
 void conv_finalize(ConvLaunch& L);
+size_t conv_swap_smem_bytes(const ConvLaunch& L, int bk);
+int conv_swap_launch(const ConvLaunch& L, int bk, int sms, cudaStream_t stream, char* err, size_t errlen);
 const char* conv_last_error();
 
 }  // namespace vgh

@@ -1,0 +1,268 @@
+// "Swapped" implicit-GEMM conv for layers with <= 128 output channels (sm_100a).
+//
+// With Cout <= 128 the natural orientation (pixels = M, Cout = N <= 128) makes every tcgen05.mma
+// read as many shared-memory bytes as an N=256 MMA for half the math, and the kernel saturates the
+// 128 B/clk shared-memory port at ~50 % of tensor peak (measured: profiles/r1_ops_*).  Here the
+// operands swap roles:  D^T[cout, pixel] = W[cout, K] * A[pixel, K]^T, i.e. M = 128 weight rows
+// (zero-padded), N = a 256-pixel (tw x th) tile.  Same smem bytes per MMA as the N=256 case, twice
+// the math.  The accumulator then has channels on TMEM lanes and pixels on columns; the epilogue
+// transposes through a shared-memory tile [pixel][channel] (conflict-free 2-byte stores: a warp
+// covers 32 consecutive channels of one pixel) which one thread hands to the TMA unit as a single
+// 4-D box store into the consumer's channel slice (image-border clipping is done by the TMA unit).
+// A residual tile, when present, is TMA-loaded into the same staging tile ahead of time and added
+// in place.
+//
+// Everything else matches conv_igemm.cu: persistent CTAs, TMA (4-D pixel box with OOB zero fill =
+// padding, traversal stride = conv stride; 2-D weight box), mbarrier ring, double-buffered TMEM.
+#include <cstdio>
+
+#include "conv_igemm.cuh"
+#include "ptx.cuh"
+
+namespace vgh {
+
+constexpr int kSwapEpiWarps = 8;
+constexpr int kSwapThreads = 64 + 32 * kSwapEpiWarps;
+
+template <int BK>
+__global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const __grid_constant__ ConvLaunch p) {
+  constexpr uint32_t kRowBytes = BK * 2;
+  constexpr uint32_t kWBytes = 128 * kRowBytes;  // weight tile: 128 cout rows
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int npix = p.tw * p.th;                                   // UMMA N (multiple of 16, <= 256)
+  const uint32_t x_bytes = static_cast<uint32_t>(npix) * kRowBytes;  // pixel tile bytes
+  const uint32_t x_slot = (x_bytes + 1023u) & ~1023u;
+  const uint32_t w_base = smem_base;
+  const uint32_t x_base = w_base + p.stages * kWBytes;
+  const uint32_t stage_base = x_base + p.stages * x_slot;                  // epilogue tile [npix][n_total] bf16
+  const uint32_t stage_bytes = static_cast<uint32_t>(npix * p.n_total) * 2;
+  const uint32_t bar_base = stage_base + ((stage_bytes + 1023u) & ~1023u);
+  const uint32_t full_bar = bar_base;
+  const uint32_t empty_bar = bar_base + 8 * p.stages;
+  const uint32_t tmem_full_bar = bar_base + 16 * p.stages;
+  const uint32_t tmem_empty_bar = tmem_full_bar + 16;
+  const uint32_t res_full_bar = tmem_empty_bar + 16;
+  const uint32_t tmem_slot = res_full_bar + 8;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar + 8 * a, 1);
+      mbar_init(tmem_empty_bar + 8 * a, kSwapEpiWarps);
+    }
+    mbar_init(res_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_dyn(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_acc;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_acc) : "r"(tmem_slot));
+
+  const int cblks = p.cin / BK;
+  const int num_kb = p.ntaps * cblks;
+  const uint32_t acc_cols = static_cast<uint32_t>(npix);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      const uint32_t tx_bytes = kWBytes + x_bytes;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        const int b_img = item / tiles_per_img;
+        const int t_in = item - b_img * tiles_per_img;
+        const int tyi = t_in / p.tiles_x;
+        const int h0 = tyi * p.th, w0 = (t_in - tyi * p.tiles_x) * p.tw;
+        int tap = 0, cb = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+          const uint32_t fb = full_bar + 8 * stage;
+          mbar_arrive_expect_tx(fb, tx_bytes);
+          const int ty = tap / p.kw;
+          const int tx = tap - ty * p.kw;
+          tma_load_4d(x_base + stage * x_slot, &p.tmA, fb, p.cin_off + cb * BK, w0 * p.stride + tx - p.pad,
+                      h0 * p.stride + ty - p.pad, b_img);
+          tma_load_2d(w_base + stage * kWBytes, &p.tmB, fb, tap * p.cin + cb * BK, 0);
+          if (++cb == cblks) {
+            cb = 0;
+            ++tap;
+          }
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      const uint32_t idesc = umma_idesc_bf16(128, static_cast<uint32_t>(npix));
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        mbar_wait(tmem_empty_bar + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_acc + acc * acc_cols;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar + 8 * stage, phase);
+          tc_fence_after();
+          const uint64_t w_desc = umma_smem_desc(w_base + stage * kWBytes, kRowBytes);  // M side: weights
+          const uint64_t x_desc = umma_smem_desc(x_base + stage * x_slot, kRowBytes);   // N side: pixels
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_bf16(d, w_desc + 2 * k, x_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(empty_bar + 8 * stage);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(tmem_full_bar + 8 * acc);
+        if (++acc == p.acc_stages) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue: lanes = channels, columns = pixels =====================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int chunk0 = ew >> 2;
+    const int ch = quarter * 32 + lane;  // output channel of this thread
+    const bool ch_ok = ch < p.n_total;
+    const float bias = ch_ok ? __ldg(p.bias + ch) : 0.f;
+    const int n_chunks = npix >> 4;
+    const bool has_res = p.res != nullptr;
+    const bool leader = (ew == 0 && lane == 0);
+    unsigned short* stile = reinterpret_cast<unsigned short*>(smem_raw + (stage_base - smem_u32(smem_raw)));
+    auto item_coords = [&](int item, int& b_img, int& h0, int& w0) {
+      b_img = item / tiles_per_img;
+      const int t_in = item - b_img * tiles_per_img;
+      const int tyi = t_in / p.tiles_x;
+      h0 = tyi * p.th;
+      w0 = (t_in - tyi * p.tiles_x) * p.tw;
+    };
+    if (has_res && leader && blockIdx.x < p.num_items) {  // residual tile of the first item
+      int b_img, h0, w0;
+      item_coords(blockIdx.x, b_img, h0, w0);
+      tma_prefetch_desc(&p.tmRes);
+      mbar_arrive_expect_tx(res_full_bar, stage_bytes);
+      tma_load_4d(stage_base, &p.tmRes, res_full_bar, p.res_coff, w0, h0, b_img);
+    }
+    if (leader) tma_prefetch_desc(&p.tmOut);
+    int acc = 0;
+    uint32_t acc_phase = 0, res_phase = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      int b_img, h0, w0;
+      item_coords(item, b_img, h0, w0);
+      mbar_wait(tmem_full_bar + 8 * acc, acc_phase);
+      tc_fence_after();
+      if (has_res) {
+        mbar_wait(res_full_bar, res_phase);
+        res_phase ^= 1;
+      }
+      const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + acc * acc_cols;
+      for (int c = chunk0; c < n_chunks; c += 2) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c * 16, v);
+        tmem_ld_wait();
+        if (ch_ok) {
+          unsigned short* sp = stile + (c * 16) * p.n_total + ch;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float x = __uint_as_float(v[j]) + bias;
+            if (p.relu) x = fmaxf(x, 0.f);
+            if (has_res) x = fmaf(p.res_alpha, __uint_as_float(static_cast<uint32_t>(sp[j * p.n_total]) << 16), x);
+            sp[j * p.n_total] = __bfloat16_as_ushort(__float2bfloat16_rn(x));
+          }
+        }
+      }
+      // TMEM drained by this warp -> MMA may reuse the accumulator stage
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty_bar + 8 * acc);
+      // hand the finished tile to the TMA unit
+      fence_proxy_async();
+      named_bar_sync(1, 32 * kSwapEpiWarps);
+      if (leader) {
+        tma_store_4d(&p.tmOut, stage_base, p.out_coff, w0, h0, b_img);
+        tma_store_commit();
+        tma_store_wait_read();  // the tile has been read out of shared memory
+        const int next = item + gridDim.x;
+        if (has_res && next < p.num_items) {
+          int nb, nh, nw;
+          item_coords(next, nb, nh, nw);
+          mbar_arrive_expect_tx(res_full_bar, stage_bytes);
+          tma_load_4d(stage_base, &p.tmRes, res_full_bar, p.res_coff, nw, nh, nb);
+        }
+      }
+      named_bar_sync(1, 32 * kSwapEpiWarps);  // nobody rewrites the tile before the store has read it
+      if (++acc == p.acc_stages) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_dyn(tmem_acc, static_cast<uint32_t>(p.tmem_cols));
+  }
+}
+
+size_t conv_swap_smem_bytes(const ConvLaunch& L, int bk) {
+  const size_t x_slot = (static_cast<size_t>(L.tw * L.th) * bk * 2 + 1023) & ~static_cast<size_t>(1023);
+  const size_t staging = (static_cast<size_t>(L.tw * L.th) * L.n_total * 2 + 1023) & ~static_cast<size_t>(1023);
+  return 1024 + static_cast<size_t>(L.stages) * (128 * bk * 2 + x_slot) + staging + 16 * L.stages + 96;
+}
+
+template <int BK>
+static int launch_swap_t(const ConvLaunch& L, int sms, cudaStream_t stream, char* err, size_t errlen) {
+  static size_t configured = 0;
+  const size_t smem = conv_swap_smem_bytes(L, BK);
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_swap_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      snprintf(err, errlen, "swap conv: set smem %zu failed: %s", smem, cudaGetErrorString(e));
+      return 4;
+    }
+    configured = smem;
+  }
+  dim3 grid(L.num_items < sms ? L.num_items : sms);
+  conv_igemm_swap_kernel<BK><<<grid, kSwapThreads, smem, stream>>>(L);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(err, errlen, "swap conv launch failed: %s", cudaGetErrorString(e));
+    return 5;
+  }
+  return 0;
+}
+
+int conv_swap_launch(const ConvLaunch& L, int bk, int sms, cudaStream_t stream, char* err, size_t errlen) {
+  if (bk == 64) return launch_swap_t<64>(L, sms, stream, err, errlen);
+  if (bk == 32) return launch_swap_t<32>(L, sms, stream, err, errlen);
+  snprintf(err, errlen, "unsupported BK %d", bk);
+  return 6;
+}
+
+}  // namespace vgh

@@ -79,6 +79,7 @@ struct OpRt {
   ConvLaunch L;
   int bk;
   int cfg_mt = 0, cfg_stages = 0, cfg_tw = 0, cfg_th = 0;  // 0 = heuristic; set by vgh_detector_autotune
+  int cfg_swap = -1;                                          // -1 = heuristic
 };
 
 struct vgh_detector {
@@ -119,6 +120,25 @@ static void pick_tile(int Ho, int Wo, int& tw, int& th) {
   }
 }
 
+// swapped mode: tile of up to 256 pixels whose pixel count is a multiple of 16 (it is the UMMA N)
+static void pick_tile_swap(int Ho, int Wo, int& tw, int& th) {
+  double best = -1.0;
+  tw = 16; th = 1;
+  for (int h = 1; h <= 256 && h <= Ho; ++h) {
+    for (int w = (256 / h < Wo ? 256 / h : Wo); w >= 1; --w) {
+      if ((w * h) % 16) continue;
+      const int tx = (Wo + w - 1) / w, ty = (Ho + h - 1) / h;
+      const double eff = static_cast<double>(Ho) * Wo / (static_cast<double>(tx) * ty * 256.0);
+      if (eff > best + 1e-9) { best = eff; tw = w; th = h; }
+      break;  // widest admissible w for this h only
+    }
+  }
+}
+
+static bool swap_eligible(const vgh_op_desc& q, const vgh_buf_desc& ob) {
+  return q.cout <= 128 && !q.up && !ob.fp32 && q.n_pad >= 128;
+}
+
 static int auto_block_n(int cout, int up, int up_cout) {
   const int lim = up ? up_cout : cout;
   if (lim <= 256) return lim;
@@ -141,7 +161,11 @@ static int build_conv(vgh_detector* d, OpRt& o) {
   L.stride = q.stride;
   L.Ho = q.up ? ib.H : (ib.H + q.stride - 1) / q.stride;
   L.Wo = q.up ? ib.W : (ib.W + q.stride - 1) / q.stride;
-  if (o.cfg_tw > 0) { L.tw = o.cfg_tw; L.th = o.cfg_th; } else pick_tile(L.Ho, L.Wo, L.tw, L.th);
+  L.swap = o.cfg_swap >= 0 ? o.cfg_swap : (swap_eligible(q, ob) && L.Ho * L.Wo >= 1024 ? 1 : 0);
+  if (L.swap && !swap_eligible(q, ob)) return fail(2, "op not eligible for the swapped kernel");
+  if (o.cfg_tw > 0) { L.tw = o.cfg_tw; L.th = o.cfg_th; }
+  else if (L.swap) pick_tile_swap(L.Ho, L.Wo, L.tw, L.th);
+  else pick_tile(L.Ho, L.Wo, L.tw, L.th);
   L.tiles_x = (L.Wo + L.tw - 1) / L.tw;
   L.tiles_y = (L.Ho + L.th - 1) / L.th;
   L.cin_off = q.in_coff;
@@ -152,7 +176,7 @@ static int build_conv(vgh_detector* d, OpRt& o) {
   L.n_total = q.cout;
   L.block_n = q.block_n > 0 ? q.block_n : auto_block_n(q.cout, q.up, q.up_cout);
   if (L.block_n % 16 || L.block_n > 256) return fail(2, "bad block_n %d", L.block_n);
-  if (q.n_pad % L.block_n) return fail(2, "n_pad %d not a multiple of block_n %d", q.n_pad, L.block_n);
+  if (q.n_pad < ((q.cout + L.block_n - 1) / L.block_n) * L.block_n) return fail(2, "n_pad %d too small for block_n %d", q.n_pad, L.block_n);
   if (q.k_total != L.ntaps * q.cin) return fail(2, "k_total mismatch");
   L.out_cstride = ob.C;
   L.out_coff = q.out_coff;
@@ -177,14 +201,25 @@ static int build_conv(vgh_detector* d, OpRt& o) {
     L.res_coff = q.res_coff;
     L.res_alpha = q.res_alpha;
   }
-  L.mt = o.cfg_mt > 0 ? o.cfg_mt : conv_default_mt(L.block_n);
-  L.stages = o.cfg_stages > 0 ? o.cfg_stages : conv_pick_stages(L.block_n, o.bk, L.mt);
+  L.mt = L.swap ? 1 : (o.cfg_mt > 0 ? o.cfg_mt : conv_default_mt(L.block_n));
+  if (L.swap) {
+    const int stage_bytes = 128 * o.bk * 2 + ((L.tw * L.th * o.bk * 2 + 1023) & ~1023);
+    const int staging = (L.tw * L.th * L.n_total * 2 + 1023) & ~1023;  // epilogue tile [pixels][channels]
+    int st = o.cfg_stages > 0 ? o.cfg_stages : (222 * 1024 - staging) / stage_bytes;
+    L.stages = st > 8 ? 8 : (st < 2 ? 2 : st);
+  } else {
+    L.stages = o.cfg_stages > 0 ? o.cfg_stages : conv_pick_stages(L.block_n, o.bk, L.mt);
+  }
   if (L.mt * L.block_n > 512) return fail(2, "mt %d x block_n %d exceeds TMEM", L.mt, L.block_n);
   conv_finalize(L);
   if (ib.fp32) return fail(2, "conv input must be bf16");
   int rc = conv_make_tensor_maps(L, d->buf_ptr[q.in_buf], ib.C, ib.H, ib.W, d->weights + q.w_off, q.k_total, q.n_pad,
                                  o.bk);
   if (rc) return fail(3, "%s", conv_last_error());
+  if (L.swap) {
+    rc = conv_make_io_maps(L, d->buf_ptr[q.out_buf], q.res_buf >= 0 ? d->buf_ptr[q.res_buf] : nullptr);
+    if (rc) return fail(3, "%s", conv_last_error());
+  }
   return 0;
 }
 
@@ -348,12 +383,26 @@ extern "C" int vgh_detector_autotune(vgh_detector* d, int iters, void* stream) {
   for (OpRt& o : d->ops) {
     if (o.d.kind != VGH_OP_CONV) continue;
     float best = 1e30f;
-    int best_mt = 0, best_st = 0;
+    int best_mt = 0, best_st = 0, best_swap = 0;
     const int bn = o.L.block_n;
+    if (swap_eligible(o.d, d->bufs[o.d.out_buf])) {
+      OpRt t = o;
+      t.cfg_swap = 1; t.cfg_mt = 0; t.cfg_stages = 0; t.cfg_tw = 0; t.cfg_th = 0;
+      if (!build_conv(d, t) && !conv_launch(t.L, t.bk, s)) {
+        cudaEventRecord(e0, s);
+        for (int i = 0; i < iters; ++i) conv_launch(t.L, t.bk, s);
+        cudaEventRecord(e1, s);
+        if (cudaStreamSynchronize(s) != cudaSuccess) return fail(7, "autotune (swap) launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        best = ms; best_swap = 1; best_mt = 1; best_st = 0;
+      }
+    }
     for (int mt : {1, 2, 4}) {
       if (mt * bn > 512) continue;
       for (int variant = 0; variant < 2; ++variant) {
         OpRt t = o;
+        t.cfg_swap = 0;
         t.cfg_mt = mt;
         const int stage_bytes = (128 * mt + bn) * t.bk * 2;
         int st = (variant == 0 ? 200 * 1024 : 100 * 1024) / stage_bytes;  // 1 CTA/SM deep vs 2 CTAs/SM
@@ -369,10 +418,11 @@ extern "C" int vgh_detector_autotune(vgh_detector* d, int iters, void* stream) {
         if (cudaStreamSynchronize(s) != cudaSuccess) return fail(7, "autotune launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
-        if (ms < best) { best = ms; best_mt = mt; best_st = st; }
+        if (ms < best) { best = ms; best_mt = mt; best_st = st; best_swap = 0; }
       }
     }
     if (best_mt) {
+      o.cfg_swap = best_swap;
       o.cfg_mt = best_mt;
       o.cfg_stages = best_st;
       int rc = build_conv(d, o);
@@ -387,7 +437,7 @@ extern "C" int vgh_detector_autotune(vgh_detector* d, int iters, void* stream) {
 extern "C" int vgh_detector_op_config(const vgh_detector* d, int op, int32_t* out6) {
   if (!d || op < 0 || op >= (int)d->ops.size() || !out6) return fail(1, "bad argument");
   const OpRt& o = d->ops[op];
-  out6[0] = o.L.mt; out6[1] = o.L.stages; out6[2] = o.L.block_n; out6[3] = o.bk; out6[4] = o.L.tw; out6[5] = o.L.th;
+  out6[0] = o.L.swap ? -1 : o.L.mt; out6[1] = o.L.stages; out6[2] = o.L.block_n; out6[3] = o.bk; out6[4] = o.L.tw; out6[5] = o.L.th;
   return 0;
 }
 
