@@ -15,7 +15,7 @@ contains configs[1] (batch 32, backbone only) entirely.
 `e2e`    : the same step through the host-buffer C-ABI call (vgh_detector_run_host): pinned host
            images -> H2D -> graph -> D2H of counts/boxes/scores/params/vertices, every step.
 `roofline`: conv_igemm kernel launches of one step timed live with CUDA-event pairs (eager pass),
-           algorithmic FLOPs (83.34 GMAC/img deploy form minus the CUDA-core stem) / that time.
+           algorithmic FLOPs (83.34 GMAC/img, deploy form) / that time.
 """
 import argparse
 import json

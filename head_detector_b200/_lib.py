@@ -39,7 +39,6 @@ class NetDesc(C.Structure):
         ("bufs", C.POINTER(BufDesc)), ("ops", C.POINTER(OpDesc)),
         ("weights_host", C.c_void_p), ("n_weights", C.c_int64),
         ("bias_host", C.c_void_p), ("n_bias", C.c_int64),
-        ("stem_w_host", C.c_void_p), ("stem_b_host", C.c_void_p),
         ("reg_buf", C.c_int32 * 3), ("flame_buf", C.c_int32 * 3),
         ("keep_k", C.c_int32),
     ]

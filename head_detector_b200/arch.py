@@ -121,8 +121,10 @@ class Plan:
 def build_plan(image_size: int = 640) -> Plan:
     P = Plan(image_size)
     S = image_size
-    stem = P.buf("stem", S // 2, 64)
-    P.ops.append(Op(_lib.OP_STEM, (0, 0, 3), (stem, 0), 64, 3, 2, 1, label="stem"))
+    cols = P.buf("stem.cols", S // 2, 32)   # im2col rows of the uint8 image: 27 taps (ky,kx,c) + 5 zeros
+    P.ops.append(Op(_lib.OP_STEM, (0, 0, 3), (cols, 0), 32, 3, 2, 0, label="stem.im2col"))
+    stem = P.buf("stem", S // 2, 64)        # 48 real channels + 16 zeros (64-wide K blocks downstream)
+    P.conv("stem", (cols, 0, 32), (stem, 0), [Part("stem", 0, STEM_OUT, [(0, 0, 27)])], cout=64)
     prev, prev_c, res = stem, 64, S // 2
     feats = []
     for i, (cout, n, hid) in enumerate(BACKBONE, start=1):
@@ -219,8 +221,6 @@ class PackedNet:
     plan: Plan
     weights: np.ndarray   # uint16 bf16 bits
     bias: np.ndarray      # float32
-    stem_w: np.ndarray    # [48,27] float32
-    stem_b: np.ndarray    # [48]
     op_meta: List[dict]
 
 
@@ -235,8 +235,10 @@ def pack(plan: Plan, w: Dict[str, torch.Tensor]) -> PackedNet:
         cin, taps = op.src[2], op.k * op.k
         block_n = _auto_block_n(op.cout, op.up, op.up_cout)
         n_pad = (op.cout + block_n - 1) // block_n * block_n
-        if op.cout <= 128 and not op.up and not plan.bufs[op.dst[0]][3]:
-            n_pad = 128  # eligible for the operand-swapped kernel (M = 128 weight rows, zero padded)
+        if not op.up:  # operand-swapped kernel: G channel groups of gw <= 128, each fetched as a 128-row box
+            G = (op.cout + 127) // 128
+            if op.cout % G == 0:
+                n_pad = max(n_pad, (op.cout // G) * (G - 1) + 128)
         M = torch.zeros(n_pad, taps, cin, dtype=torch.float32)
         bvec = torch.zeros(n_pad, dtype=torch.float32)
         for p in op.parts:
@@ -248,6 +250,10 @@ def pack(plan: Plan, w: Dict[str, torch.Tensor]) -> PackedNet:
                         sub = dy * 2 + dx
                         M[sub * co:(sub + 1) * co, 0, :] = wt[:, :, dy, dx].T
                         bvec[sub * co:(sub + 1) * co] = bt
+                continue
+            if p.name == "stem":  # 3x3x3 taps flattened (ky,kx,c) into the K columns; /255 of detector.py:51 folded in
+                M[p.row:p.row + p.cout, 0, 0:27] = wt.permute(0, 2, 3, 1).reshape(p.cout, 27) / 255.0
+                bvec[p.row:p.row + p.cout] = bt
                 continue
             assert wt.shape[0] == p.cout and wt.shape[2] == op.k, (p.name, tuple(wt.shape), p.cout, op.k)
             assert sum(s[2] for s in p.segs) == wt.shape[1], (p.name, p.segs, wt.shape)
@@ -265,9 +271,7 @@ def pack(plan: Plan, w: Dict[str, torch.Tensor]) -> PackedNet:
         meta.append(dict(w_off=w_off, b_off=b_off, n_pad=n_pad, k_total=taps * cin, block_n=block_n, alpha=alpha))
         w_off += chunk.size
         b_off += n_pad
-    sw = w["stem.w"].float().permute(0, 2, 3, 1).reshape(STEM_OUT, 27) / 255.0  # (ky,kx,c); detector.py:51 folded
-    return PackedNet(plan, np.concatenate(wchunks), np.concatenate(bchunks), np.ascontiguousarray(sw.numpy()),
-                     np.ascontiguousarray(w["stem.b"].float().numpy()), meta)
+    return PackedNet(plan, np.concatenate(wchunks), np.concatenate(bchunks), meta)
 
 
 def conv_names() -> List[Tuple[str, int, int, int, bool]]:
@@ -275,6 +279,8 @@ def conv_names() -> List[Tuple[str, int, int, int, bool]]:
     out = [("stem", 3, 3, STEM_OUT, False)]
     for op in build_plan(640).ops:
         for p in op.parts:
+            if p.name == "stem":
+                continue
             cin = sum(s[2] for s in p.segs)
             out.append((p.name, 2 if p.transposed else op.k, cin, p.cout // 4 if p.transposed else p.cout, p.transposed))
     return out
@@ -310,6 +316,8 @@ def total_macs(image_size: int = 640) -> int:
         src_res = P.bufs[op.src[0]][0]
         out_res = src_res if op.up else src_res // op.stride
         for p in op.parts:
+            if p.name == "stem":
+                continue  # counted above with its true K = 27
             cin = sum(s[2] for s in p.segs)
             tot += cin * p.cout * out_res * out_res * (1 if p.transposed else op.k * op.k)
     return tot

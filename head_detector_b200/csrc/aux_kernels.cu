@@ -1,4 +1,4 @@
-// Small CUDA-core kernels around the tensor-core convs (sm_100a): stem conv on uint8 input, SPP
+// Small CUDA-core kernels around the tensor-core convs (sm_100a): stem im2col of the uint8 input, SPP
 // max-pools, DFL/sigmoid box decode, FLAME-row assembly (dense or for NMS survivors only).
 // All HBM-bound elementwise/stencil work: coalesced 16-byte accesses, no reshaping into GEMMs.
 #include <cuda_bf16.h>
@@ -12,79 +12,52 @@
 namespace vgh {
 
 // ---------------------------------------------------------------------------------------- stem
-// 3x3 stride-2 pad-1 conv, 3 -> 48 channels, ReLU; input uint8 NHWC (the /255 of detector.py:51 is
-// folded into the fp32 weights), output bf16 NHWC with 64 channels (48 real + 16 zeros so that the
-// next layer's K blocks are 64 wide).  thread = one output pixel, all 48 channels in 3 passes of 16.
-__global__ void __launch_bounds__(128) stem_conv_kernel(const uint8_t* __restrict__ img, const float* __restrict__ w,
-                                                        const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
+// The 3x3 stride-2 stem (3 -> 48 channels) has K = 27: too small for a TMA/UMMA K block fed from the
+// uint8 image directly.  This kernel expands each output pixel's 27 input bytes (ky,kx,c order, zero
+// outside the image = conv padding) to a 32-wide bf16 row (5 zero columns); the stem then runs on
+// the tensor cores as a 1x1 conv with Cin = 32 whose weights carry the /255 of detector.py:51.
+// uint8 -> bf16 is exact.
+__global__ void __launch_bounds__(256) stem_pack_kernel(const uint8_t* __restrict__ img, __nv_bfloat16* __restrict__ out,
                                                         int B, int S) {
-  // weights transposed to [tap][48] so that 4 output channels come from one broadcast 128-bit load
-  __shared__ __align__(16) float ws[27 * 48];
-  __shared__ __align__(16) float bs[48];
-  for (int i = threadIdx.x; i < 48 * 27; i += blockDim.x) {
-    const int co = i / 27, t = i - co * 27;
-    ws[t * 48 + co] = w[i];
-  }
-  for (int i = threadIdx.x; i < 48; i += blockDim.x) bs[i] = bias[i];
-  __syncthreads();
+  // thread = one output pixel: its 3x3x3 window is three runs of 9 consecutive bytes (one per image row)
   const int Ho = S >> 1;
-  const long long total_pix = static_cast<long long>(B) * Ho * Ho;
   const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (pix >= total_pix) return;
+  const long long total = static_cast<long long>(B) * Ho * Ho;
+  if (pix >= total) return;
   const int ow = static_cast<int>(pix % Ho);
   const int oh = static_cast<int>((pix / Ho) % Ho);
   const int b = static_cast<int>(pix / (static_cast<long long>(Ho) * Ho));
-  float x[27];
+  float x[32];
+#pragma unroll
+  for (int i = 27; i < 32; ++i) x[i] = 0.f;
+  const int iw0 = 2 * ow - 1;
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
     const int ih = 2 * oh + ky - 1;
     const bool row_ok = ih >= 0 && ih < S;
-    const uint8_t* rowp = img + (static_cast<size_t>(b) * S + (row_ok ? ih : 0)) * S * 3;
+    const uint8_t* p = img + ((static_cast<size_t>(b) * S + (row_ok ? ih : 0)) * S + iw0) * 3;
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      const int iw = 2 * ow + kx - 1;
-      const bool ok = row_ok && iw >= 0 && iw < S;
-      const uint8_t* p = rowp + (ok ? iw : 0) * 3;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) x[(ky * 3 + kx) * 3 + c] = ok ? static_cast<float>(__ldg(p + c)) : 0.f;
+    for (int j = 0; j < 9; ++j) {
+      const bool ok = row_ok && (j >= 3 || iw0 >= 0) && (iw0 + j / 3 < S);
+      x[ky * 9 + j] = ok ? static_cast<float>(__ldg(p + j)) : 0.f;
     }
   }
-  uint4* op = reinterpret_cast<uint4*>(out + pix * 64);
-#pragma unroll 1
-  for (int g = 0; g < 3; ++g) {  // 16 output channels per pass
-    float acc[16];
+  uint4* op = reinterpret_cast<uint4*>(out + pix * 32);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = bs[g * 16 + j];
+  for (int u = 0; u < 4; ++u) {
+    uint32_t w[4];
 #pragma unroll
-    for (int t = 0; t < 27; ++t) {
-      const float4* wp = reinterpret_cast<const float4*>(ws + t * 48 + g * 16);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 w4 = wp[q];
-        acc[4 * q] = fmaf(w4.x, x[t], acc[4 * q]);
-        acc[4 * q + 1] = fmaf(w4.y, x[t], acc[4 * q + 1]);
-        acc[4 * q + 2] = fmaf(w4.z, x[t], acc[4 * q + 2]);
-        acc[4 * q + 3] = fmaf(w4.w, x[t], acc[4 * q + 3]);
-      }
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(x[u * 8 + 2 * i], x[u * 8 + 2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
     }
-    uint32_t packed[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(acc[2 * j], 0.f), fmaxf(acc[2 * j + 1], 0.f));
-      packed[j] = *reinterpret_cast<uint32_t*>(&h);
-    }
-    op[2 * g] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-    op[2 * g + 1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+    op[u] = make_uint4(w[0], w[1], w[2], w[3]);
   }
-  op[6] = make_uint4(0, 0, 0, 0);  // channels 48..63: zero padding (next layer's K blocks are 64 wide)
-  op[7] = make_uint4(0, 0, 0, 0);
 }
 
-int stem_conv_launch(const uint8_t* img, const float* w, const float* bias, __nv_bfloat16* out, int B, int S,
-                     cudaStream_t stream) {
-  const long long Ho = S / 2;
-  const long long total = static_cast<long long>(B) * Ho * Ho;
-  stem_conv_kernel<<<static_cast<int>((total + 127) / 128), 128, 0, stream>>>(img, w, bias, out, B, S);
+int stem_pack_launch(const uint8_t* img, __nv_bfloat16* out, int B, int S, cudaStream_t stream) {
+  const long long total = static_cast<long long>(B) * (S / 2) * (S / 2);
+  stem_pack_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, stream>>>(img, out, B, S);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

@@ -17,8 +17,7 @@ struct DecodeLevels {
   int reg_cstride, flame_cstride;
 };
 
-int stem_conv_launch(const uint8_t* img, const float* w, const float* bias, __nv_bfloat16* out, int B, int S,
-                     cudaStream_t stream);
+int stem_pack_launch(const uint8_t* img, __nv_bfloat16* out, int B, int S, cudaStream_t stream);
 int spp_pool_launch(__nv_bfloat16* buf, int B, int H, int W, int C, cudaStream_t stream);
 int box_decode_launch(const DecodeLevels& lv, float* boxes, float* scores, int B, int A, cudaStream_t stream);
 int flame_dense_launch(const DecodeLevels& lv, float* out, int B, int A, cudaStream_t stream);

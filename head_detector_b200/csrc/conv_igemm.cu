@@ -1,6 +1,7 @@
 #include "conv_igemm.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "ptx.cuh"
@@ -71,6 +72,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   tc_fence_after();
   uint32_t tmem_acc;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_acc) : "r"(tmem_slot));
+  // everything above overlapped the previous kernel's tail (PDL); its outputs are needed from here on
+  pdl_wait();
+  pdl_launch_dependents();
 
   const int cblks = p.cin / BK;
   const int num_kb = p.ntaps * cblks;
@@ -286,6 +290,16 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// PDL can be switched off with VGGHEADS_B200_NO_PDL=1 (debugging aid)
+bool conv_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("VGGHEADS_B200_NO_PDL");
+    on = (e && e[0] == '1') ? 0 : 1;
+  }
+  return on == 1;
+}
+
 static int g_num_sms = 0;
 static int num_sms() {
   if (g_num_sms == 0) {
@@ -324,7 +338,7 @@ void conv_finalize(ConvLaunch& L) {
   if (L.swap) {  // one item = one (tw x th)-pixel tile; all (<=128) output channels
     L.mt = 1;
     L.n_tiles = 1;
-    L.num_items = L.tiles_x * L.tiles_y * L.B;
+    L.num_items = L.tiles_x * L.tiles_y * L.B * L.ngroups;
     const int npix = L.tw * L.th;
     L.acc_stages = (2 * npix <= 512) ? 2 : 1;
     int cols = 32;
@@ -386,9 +400,12 @@ int conv_make_io_maps(ConvLaunch& L, void* out_base, const void* res_base) {
     const int C = which == 0 ? L.out_cstride : L.res_cstride;
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)L.Wo, (cuuint64_t)L.Ho, (cuuint64_t)L.B};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)L.Wo * C * 2, (cuuint64_t)L.Ho * L.Wo * C * 2};
-    cuuint32_t box[4] = {(cuuint32_t)L.n_total, (cuuint32_t)L.tw, (cuuint32_t)L.th, 1};
+    const bool f32 = which == 0 && L.out_fp32;
+    const cuuint64_t es = f32 ? 4 : 2;
+    strides[0] = (cuuint64_t)C * es; strides[1] = (cuuint64_t)L.Wo * C * es; strides[2] = (cuuint64_t)L.Ho * L.Wo * C * es;
+    cuuint32_t box[4] = {(cuuint32_t)L.gw, (cuuint32_t)L.tw, (cuuint32_t)L.th, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(which == 0 ? &L.tmOut : &L.tmRes, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims,
+    CUresult r = enc(which == 0 ? &L.tmOut : &L.tmRes, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims,
                      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -412,9 +429,18 @@ static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
     }
     configured = smem;
   }
-  dim3 grid(L.num_items < num_sms() ? L.num_items : num_sms());
-  conv_igemm_kernel<BK><<<grid, kThreads, smem, stream>>>(L);
-  cudaError_t e = cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(L.num_items < num_sms() ? L.num_items : num_sms());
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = conv_pdl_enabled() ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BK>, L);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(g_conv_err, sizeof(g_conv_err), "conv launch failed: %s", cudaGetErrorString(e));
     return 5;

@@ -39,6 +39,8 @@ struct ConvLaunch {
   int stages, tmem_cols;
   int mt;                        // M tiles (128-pixel accumulators) per work item sharing one weight stream
   int swap;                      // 1: operands swapped (conv_igemm_swap.cu): M = 128 cout rows, N = tw*th pixels
+  int ngroups, gw;               // swapped kernel: output-channel groups and channels per group (<= 128)
+  int stg_bufs;                  // swapped kernel: epilogue staging tiles (2 = store of item i overlaps item i+1)
   int acc_stages, n_tiles, num_items;  // TMEM accumulator stages (1|2), N tiles, work items (persistent CTAs)
 };
 
@@ -52,6 +54,7 @@ size_t conv_smem_bytes(const ConvLaunch& L, int bk);
 int conv_pick_stages(int block_n, int bk, int mt);
 int conv_default_mt(int block_n);
 void conv_finalize(ConvLaunch& L);
+bool conv_pdl_enabled();
 size_t conv_swap_smem_bytes(const ConvLaunch& L, int bk);
 int conv_swap_launch(const ConvLaunch& L, int bk, int sms, cudaStream_t stream, char* err, size_t errlen);
 const char* conv_last_error();

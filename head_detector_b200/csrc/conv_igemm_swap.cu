@@ -1,4 +1,4 @@
-// "Swapped" implicit-GEMM conv for layers with <= 128 output channels (sm_100a).
+// "Swapped" implicit-GEMM conv: output channels on the MMA M side, in groups of <= 128 (sm_100a).
 //
 // With Cout <= 128 the natural orientation (pixels = M, Cout = N <= 128) makes every tcgen05.mma
 // read as many shared-memory bytes as an N=256 MMA for half the math, and the kernel saturates the
@@ -11,6 +11,10 @@
 // 4-D box store into the consumer's channel slice (image-border clipping is done by the TMA unit).
 // A residual tile, when present, is TMA-loaded into the same staging tile ahead of time and added
 // in place.
+//
+// Layers with more than 128 output channels run as G equal channel groups (work item = pixel tile x
+// group; the groups of one tile run on neighbouring CTAs at the same time, so the pixel tile is read
+// from HBM once).  fp32 outputs (raw head tensors) use the same path with a 4-byte staging tile.
 //
 // Everything else matches conv_igemm.cu: persistent CTAs, TMA (4-D pixel box with OOB zero fill =
 // padding, traversal stride = conv stride; 2-D weight box), mbarrier ring, double-buffered TMEM.
@@ -36,14 +40,18 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
   const uint32_t w_base = smem_base;
   const uint32_t x_base = w_base + p.stages * kWBytes;
   const uint32_t stage_base = x_base + p.stages * x_slot;                  // epilogue tile [npix][n_total] bf16
-  const uint32_t stage_bytes = static_cast<uint32_t>(npix * p.n_total) * 2;
-  const uint32_t bar_base = stage_base + ((stage_bytes + 1023u) & ~1023u);
+  const int gw = p.gw;                                                     // channels per group (<= 128)
+  const uint32_t esz = p.out_fp32 ? 4u : 2u;
+  const uint32_t stage_bytes = static_cast<uint32_t>(npix * gw) * esz;
+  const uint32_t stage_slot = (stage_bytes + 1023u) & ~1023u;
+  const int stg_bufs = p.stg_bufs;                                         // 1 or 2 epilogue tiles
+  const uint32_t bar_base = stage_base + stg_bufs * stage_slot;
   const uint32_t full_bar = bar_base;
   const uint32_t empty_bar = bar_base + 8 * p.stages;
   const uint32_t tmem_full_bar = bar_base + 16 * p.stages;
   const uint32_t tmem_empty_bar = tmem_full_bar + 16;
-  const uint32_t res_full_bar = tmem_empty_bar + 16;
-  const uint32_t tmem_slot = res_full_bar + 8;
+  const uint32_t res_full_bar = tmem_empty_bar + 16;  // [2]
+  const uint32_t tmem_slot = res_full_bar + 16;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -61,6 +69,7 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
       mbar_init(tmem_empty_bar + 8 * a, kSwapEpiWarps);
     }
     mbar_init(res_full_bar, 1);
+    mbar_init(res_full_bar + 8, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -72,6 +81,9 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
   tc_fence_after();
   uint32_t tmem_acc;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_acc) : "r"(tmem_slot));
+  // everything above overlapped the previous kernel's tail (PDL); its outputs are needed from here on
+  pdl_wait();
+  pdl_launch_dependents();
 
   const int cblks = p.cin / BK;
   const int num_kb = p.ntaps * cblks;
@@ -84,8 +96,10 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
       int stage = 0;
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-        const int b_img = item / tiles_per_img;
-        const int t_in = item - b_img * tiles_per_img;
+        const int tile = item / p.ngroups;
+        const int n_base = (item - tile * p.ngroups) * gw;
+        const int b_img = tile / tiles_per_img;
+        const int t_in = tile - b_img * tiles_per_img;
         const int tyi = t_in / p.tiles_x;
         const int h0 = tyi * p.th, w0 = (t_in - tyi * p.tiles_x) * p.tw;
         int tap = 0, cb = 0;
@@ -97,7 +111,7 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
           const int tx = tap - ty * p.kw;
           tma_load_4d(x_base + stage * x_slot, &p.tmA, fb, p.cin_off + cb * BK, w0 * p.stride + tx - p.pad,
                       h0 * p.stride + ty - p.pad, b_img);
-          tma_load_2d(w_base + stage * kWBytes, &p.tmB, fb, tap * p.cin + cb * BK, 0);
+          tma_load_2d(w_base + stage * kWBytes, &p.tmB, fb, tap * p.cin + cb * BK, n_base);
           if (++cb == cblks) {
             cb = 0;
             ++tap;
@@ -146,52 +160,65 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
     const int ew = warp - 2;
     const int quarter = warp & 3;
     const int chunk0 = ew >> 2;
-    const int ch = quarter * 32 + lane;  // output channel of this thread
-    const bool ch_ok = ch < p.n_total;
-    const float bias = ch_ok ? __ldg(p.bias + ch) : 0.f;
+    const int ch = quarter * 32 + lane;  // output channel of this thread inside its group
+    const bool ch_ok = ch < gw;
     const int n_chunks = npix >> 4;
     const bool has_res = p.res != nullptr;
     const bool leader = (ew == 0 && lane == 0);
-    unsigned short* stile = reinterpret_cast<unsigned short*>(smem_raw + (stage_base - smem_u32(smem_raw)));
+    uint8_t* stile0 = smem_raw + (stage_base - smem_u32(smem_raw));
     auto item_coords = [&](int item, int& b_img, int& h0, int& w0) {
-      b_img = item / tiles_per_img;
-      const int t_in = item - b_img * tiles_per_img;
+      const int tile = item / p.ngroups;
+      b_img = tile / tiles_per_img;
+      const int t_in = tile - b_img * tiles_per_img;
       const int tyi = t_in / p.tiles_x;
       h0 = tyi * p.th;
       w0 = (t_in - tyi * p.tiles_x) * p.tw;
     };
-    if (has_res && leader && blockIdx.x < p.num_items) {  // residual tile of the first item
+    if (has_res && leader && blockIdx.x < p.num_items) {  // residual tile of the first item -> buffer 0
       int b_img, h0, w0;
       item_coords(blockIdx.x, b_img, h0, w0);
       tma_prefetch_desc(&p.tmRes);
       mbar_arrive_expect_tx(res_full_bar, stage_bytes);
-      tma_load_4d(stage_base, &p.tmRes, res_full_bar, p.res_coff, w0, h0, b_img);
+      tma_load_4d(stage_base, &p.tmRes, res_full_bar, p.res_coff + (blockIdx.x % p.ngroups) * gw, w0, h0, b_img);
     }
     if (leader) tma_prefetch_desc(&p.tmOut);
-    int acc = 0;
-    uint32_t acc_phase = 0, res_phase = 0;
+    int acc = 0, sb = 0;
+    uint32_t acc_phase = 0, res_phase[2] = {0, 0};
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       int b_img, h0, w0;
       item_coords(item, b_img, h0, w0);
+      const int n_base = (item % p.ngroups) * gw;
+      const float bias = ch_ok ? __ldg(p.bias + n_base + ch) : 0.f;
       mbar_wait(tmem_full_bar + 8 * acc, acc_phase);
       tc_fence_after();
       if (has_res) {
-        mbar_wait(res_full_bar, res_phase);
-        res_phase ^= 1;
+        mbar_wait(res_full_bar + 8 * sb, res_phase[sb]);
+        res_phase[sb] ^= 1;
       }
+      uint8_t* stile = stile0 + sb * stage_slot;
       const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + acc * acc_cols;
       for (int c = chunk0; c < n_chunks; c += 2) {
         uint32_t v[16];
         tmem_ld16(taddr + c * 16, v);
         tmem_ld_wait();
         if (ch_ok) {
-          unsigned short* sp = stile + (c * 16) * p.n_total + ch;
+          if (p.out_fp32) {
+            float* sp = reinterpret_cast<float*>(stile) + (c * 16) * gw + ch;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float x = __uint_as_float(v[j]) + bias;
-            if (p.relu) x = fmaxf(x, 0.f);
-            if (has_res) x = fmaf(p.res_alpha, __uint_as_float(static_cast<uint32_t>(sp[j * p.n_total]) << 16), x);
-            sp[j * p.n_total] = __bfloat16_as_ushort(__float2bfloat16_rn(x));
+            for (int j = 0; j < 16; ++j) {
+              float x = __uint_as_float(v[j]) + bias;
+              if (p.relu) x = fmaxf(x, 0.f);
+              sp[j * gw] = x;
+            }
+          } else {
+            unsigned short* sp = reinterpret_cast<unsigned short*>(stile) + (c * 16) * gw + ch;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float x = __uint_as_float(v[j]) + bias;
+              if (p.relu) x = fmaxf(x, 0.f);
+              if (has_res) x = fmaf(p.res_alpha, __uint_as_float(static_cast<uint32_t>(sp[j * gw]) << 16), x);
+              sp[j * gw] = __bfloat16_as_ushort(__float2bfloat16_rn(x));
+            }
           }
         }
       }
@@ -202,24 +229,28 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
       // hand the finished tile to the TMA unit
       fence_proxy_async();
       named_bar_sync(1, 32 * kSwapEpiWarps);
+      const int nsb = stg_bufs == 2 ? (sb ^ 1) : sb;
       if (leader) {
-        tma_store_4d(&p.tmOut, stage_base, p.out_coff, w0, h0, b_img);
+        tma_store_4d(&p.tmOut, stage_base + sb * stage_slot, p.out_coff + n_base, w0, h0, b_img);
         tma_store_commit();
-        tma_store_wait_read();  // the tile has been read out of shared memory
+        // the tile the NEXT item writes must have been read out by its previous store
+        if (stg_bufs == 2) tma_store_wait_read_keep1(); else tma_store_wait_read();
         const int next = item + gridDim.x;
         if (has_res && next < p.num_items) {
           int nb, nh, nw;
           item_coords(next, nb, nh, nw);
-          mbar_arrive_expect_tx(res_full_bar, stage_bytes);
-          tma_load_4d(stage_base, &p.tmRes, res_full_bar, p.res_coff, nw, nh, nb);
+          mbar_arrive_expect_tx(res_full_bar + 8 * nsb, stage_bytes);
+          tma_load_4d(stage_base + nsb * stage_slot, &p.tmRes, res_full_bar + 8 * nsb, p.res_coff + (next % p.ngroups) * gw, nw, nh, nb);
         }
       }
-      named_bar_sync(1, 32 * kSwapEpiWarps);  // nobody rewrites the tile before the store has read it
+      named_bar_sync(1, 32 * kSwapEpiWarps);
+      sb = nsb;
       if (++acc == p.acc_stages) {
         acc = 0;
         acc_phase ^= 1;
       }
     }
+    if (leader) tma_store_wait_read();  // shared memory must outlive the last store's read
   }
 
   tc_fence_before();
@@ -232,8 +263,8 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
 
 size_t conv_swap_smem_bytes(const ConvLaunch& L, int bk) {
   const size_t x_slot = (static_cast<size_t>(L.tw * L.th) * bk * 2 + 1023) & ~static_cast<size_t>(1023);
-  const size_t staging = (static_cast<size_t>(L.tw * L.th) * L.n_total * 2 + 1023) & ~static_cast<size_t>(1023);
-  return 1024 + static_cast<size_t>(L.stages) * (128 * bk * 2 + x_slot) + staging + 16 * L.stages + 96;
+  const size_t staging = (static_cast<size_t>(L.tw * L.th) * L.gw * (L.out_fp32 ? 4 : 2) + 1023) & ~static_cast<size_t>(1023);
+  return 1024 + static_cast<size_t>(L.stages) * (128 * bk * 2 + x_slot) + L.stg_bufs * staging + 16 * L.stages + 128;
 }
 
 template <int BK>
@@ -248,9 +279,18 @@ static int launch_swap_t(const ConvLaunch& L, int sms, cudaStream_t stream, char
     }
     configured = smem;
   }
-  dim3 grid(L.num_items < sms ? L.num_items : sms);
-  conv_igemm_swap_kernel<BK><<<grid, kSwapThreads, smem, stream>>>(L);
-  cudaError_t e = cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(L.num_items < sms ? L.num_items : sms);
+  cfg.blockDim = dim3(kSwapThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = conv_pdl_enabled() ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm_swap_kernel<BK>, L);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(err, errlen, "swap conv launch failed: %s", cudaGetErrorString(e));
     return 5;

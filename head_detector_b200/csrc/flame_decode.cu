@@ -167,15 +167,22 @@ __global__ void __launch_bounds__(kTileV* HG) flame_decode_kernel(const FlameArg
     st_s[tid * 8 + 4] = xf[0]; st_s[tid * 8 + 5] = xf[1]; st_s[tid * 8 + 6] = xf[2];
   }
   __syncthreads();
-  // jaw joint J2 = J2_template + JS2 . beta ; tJ = J2 - R2 . J2
-  if (tid < kHeads * 3) {
-    const int h = tid / 3, k = tid - h * 3;
-    double acc = a.c.j2t[k];
-    for (int i = 0; i < lb; ++i) {
-      const int l = i < a.ns ? i : 300 + (i - a.ns);
-      acc = fma(a.c.js2[k * kL + l], beta_s[i * kHeads + h], acc);
+  // jaw joint J2 = J2_template + JS2 . beta ; tJ = J2 - R2 . J2.  Four lanes share one (head, coord)
+  // dot product so the 192..400-term chain of dependent L2 loads is four times shorter.
+  {
+    const int o = tid >> 2, part = tid & 3;
+    const bool live = o < kHeads * 3;
+    const int h = live ? o / 3 : 0, k = live ? o - h * 3 : 0;
+    double acc = 0.0;
+    if (live) {
+      for (int i = part; i < lb; i += 4) {
+        const int l = i < a.ns ? i : 300 + (i - a.ns);
+        acc = fma(a.c.js2[k * kL + l], beta_s[i * kHeads + h], acc);
+      }
     }
-    tj_s[tid] = acc;  // temporarily J2
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (live && part == 0) tj_s[o] = a.c.j2t[k] + acc;  // temporarily J2
   }
   __syncthreads();
   if (tid < kHeads) {

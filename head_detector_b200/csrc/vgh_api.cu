@@ -90,8 +90,6 @@ struct vgh_detector {
   std::vector<OpRt> ops;
   __nv_bfloat16* weights = nullptr;
   float* bias = nullptr;
-  float* stem_w = nullptr;
-  float* stem_b = nullptr;
   DecodeLevels lv;
   const vgh_flame* flame = nullptr;
   uint8_t* input = nullptr;
@@ -135,8 +133,20 @@ static void pick_tile_swap(int Ho, int Wo, int& tw, int& th) {
   }
 }
 
+// swapped kernel: G equal output-channel groups of gw <= 128 channels; a group's TMA box must be a
+// multiple of 16 bytes and the weight matrix must have 128 rows from every group start
+static bool swap_groups(const vgh_op_desc& q, const vgh_buf_desc& ob, int& G, int& gw) {
+  if (q.up) return false;
+  G = (q.cout + 127) / 128;
+  if (q.cout % G) return false;
+  gw = q.cout / G;
+  if ((gw * (ob.fp32 ? 4 : 2)) % 16) return false;
+  return q.n_pad >= gw * (G - 1) + 128;
+}
 static bool swap_eligible(const vgh_op_desc& q, const vgh_buf_desc& ob) {
-  return q.cout <= 128 && !q.up && !ob.fp32 && q.n_pad >= 128;
+  int G, gw;
+  if (!swap_groups(q, ob, G, gw)) return false;
+  return !(q.res_buf >= 0 && ob.fp32);
 }
 
 static int auto_block_n(int cout, int up, int up_cout) {
@@ -161,7 +171,8 @@ static int build_conv(vgh_detector* d, OpRt& o) {
   L.stride = q.stride;
   L.Ho = q.up ? ib.H : (ib.H + q.stride - 1) / q.stride;
   L.Wo = q.up ? ib.W : (ib.W + q.stride - 1) / q.stride;
-  L.swap = o.cfg_swap >= 0 ? o.cfg_swap : (swap_eligible(q, ob) && L.Ho * L.Wo >= 1024 ? 1 : 0);
+  L.swap = o.cfg_swap >= 0 ? o.cfg_swap : (swap_eligible(q, ob) && q.cout <= 128 && !ob.fp32 && L.Ho * L.Wo >= 1024 ? 1 : 0);
+  if (L.swap) swap_groups(q, ob, L.ngroups, L.gw);
   if (L.swap && !swap_eligible(q, ob)) return fail(2, "op not eligible for the swapped kernel");
   if (o.cfg_tw > 0) { L.tw = o.cfg_tw; L.th = o.cfg_th; }
   else if (L.swap) pick_tile_swap(L.Ho, L.Wo, L.tw, L.th);
@@ -204,8 +215,11 @@ static int build_conv(vgh_detector* d, OpRt& o) {
   L.mt = L.swap ? 1 : (o.cfg_mt > 0 ? o.cfg_mt : conv_default_mt(L.block_n));
   if (L.swap) {
     const int stage_bytes = 128 * o.bk * 2 + ((L.tw * L.th * o.bk * 2 + 1023) & ~1023);
-    const int staging = (L.tw * L.th * L.n_total * 2 + 1023) & ~1023;  // epilogue tile [pixels][channels]
-    int st = o.cfg_stages > 0 ? o.cfg_stages : (222 * 1024 - staging) / stage_bytes;
+    const int staging = (L.tw * L.th * L.gw * (ob.fp32 ? 4 : 2) + 1023) & ~1023;  // epilogue tile [pixels][channels]
+    const int num_kb = L.ntaps * (q.cin / o.bk);
+    // shallow-K layers are epilogue-bound: give them a second staging tile; deep-K layers need the stages
+    L.stg_bufs = (num_kb <= 8 && 2 * staging + 3 * stage_bytes <= 220 * 1024) ? 2 : 1;
+    int st = o.cfg_stages > 0 ? o.cfg_stages : (222 * 1024 - L.stg_bufs * staging) / stage_bytes;
     L.stages = st > 8 ? 8 : (st < 2 ? 2 : st);
   } else {
     L.stages = o.cfg_stages > 0 ? o.cfg_stages : conv_pick_stages(L.block_n, o.bk, L.mt);
@@ -228,7 +242,7 @@ extern "C" void vgh_detector_destroy(vgh_detector* d) {
   if (d->graph) cudaGraphExecDestroy(d->graph);
   if (d->cap_stream) cudaStreamDestroy(d->cap_stream);
   for (void* p : d->buf_ptr) cudaFree(p);
-  void* ptrs[] = {d->weights, d->bias, d->stem_w, d->stem_b, d->input, d->boxes, d->scores, d->keep_boxes,
+  void* ptrs[] = {d->weights, d->bias, d->input, d->boxes, d->scores, d->keep_boxes,
                   d->keep_scores, d->keep_idx, d->keep_cnt, d->offsets, d->head_img, d->params, d->head_xform,
                   d->verts, d->rot, d->img_xform};
   for (void* p : ptrs) cudaFree(p);
@@ -264,13 +278,10 @@ extern "C" int vgh_detector_create(const vgh_net_desc* n, const vgh_flame* flame
     d->buf_ptr.push_back(p);
     d->buf_bytes.push_back(bytes);
   }
-  if (dmalloc(&d->weights, (size_t)n->n_weights) != cudaSuccess || dmalloc(&d->bias, (size_t)n->n_bias) != cudaSuccess ||
-      dmalloc(&d->stem_w, 48 * 27) != cudaSuccess || dmalloc(&d->stem_b, 48) != cudaSuccess)
+  if (dmalloc(&d->weights, (size_t)n->n_weights) != cudaSuccess || dmalloc(&d->bias, (size_t)n->n_bias) != cudaSuccess)
     return bail(fail(4, "weight allocation failed"));
   cudaMemcpy(d->weights, n->weights_host, n->n_weights * 2, cudaMemcpyHostToDevice);
   cudaMemcpy(d->bias, n->bias_host, n->n_bias * 4, cudaMemcpyHostToDevice);
-  cudaMemcpy(d->stem_w, n->stem_w_host, 48 * 27 * 4, cudaMemcpyHostToDevice);
-  cudaMemcpy(d->stem_b, n->stem_b_host, 48 * 4, cudaMemcpyHostToDevice);
 
   for (int i = 0; i < n->n_ops; ++i) {
     OpRt o;
@@ -324,8 +335,7 @@ static int run_forward(vgh_detector* d, const uint8_t* images, cudaStream_t s, i
     int rc = 0;
     switch (o.d.kind) {
       case VGH_OP_STEM:
-        rc = stem_conv_launch(images, d->stem_w, d->stem_b, static_cast<__nv_bfloat16*>(d->buf_ptr[o.d.out_buf]), d->B,
-                              d->S, s);
+        rc = stem_pack_launch(images, static_cast<__nv_bfloat16*>(d->buf_ptr[o.d.out_buf]), d->B, d->S, s);
         if (rc) return fail(5, "stem launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         break;
       case VGH_OP_CONV:
@@ -458,7 +468,7 @@ extern "C" int vgh_detector_profile(vgh_detector* d, int iters, float conf_thr, 
     for (int i = 0; i < n_ops && !rc; ++i) {
       OpRt& o = d->ops[i];
       if (o.d.kind == VGH_OP_STEM)
-        rc = stem_conv_launch(d->input, d->stem_w, d->stem_b, static_cast<__nv_bfloat16*>(d->buf_ptr[o.d.out_buf]), d->B, d->S, s);
+        rc = stem_pack_launch(d->input, static_cast<__nv_bfloat16*>(d->buf_ptr[o.d.out_buf]), d->B, d->S, s);
       else if (o.d.kind == VGH_OP_CONV)
         rc = conv_launch(o.L, o.bk, s);
       else

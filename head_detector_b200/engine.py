@@ -42,7 +42,6 @@ class Engine:
         nd.bufs, nd.ops = bufs, ops
         nd.weights_host, nd.n_weights = pk.weights.ctypes.data, pk.weights.size
         nd.bias_host, nd.n_bias = pk.bias.ctypes.data, pk.bias.size
-        nd.stem_w_host, nd.stem_b_host = pk.stem_w.ctypes.data, pk.stem_b.ctypes.data
         nd.reg_buf = (C.c_int32 * 3)(*self.plan.reg_buf)
         nd.flame_buf = (C.c_int32 * 3)(*self.plan.flame_buf)
         nd.keep_k = self.keep_k

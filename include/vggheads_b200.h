@@ -74,6 +74,8 @@ typedef struct {
   int32_t fp32;      /* 0 = bf16, 1 = fp32 (raw head outputs) */
 } vgh_buf_desc;
 
+/* VGH_OP_STEM: im2col of the uint8 image for the 3x3 stride-2 stem -> bf16 [B,S/2,S/2,32] (27 taps in
+ * (ky,kx,c) order + 5 zeros); the stem itself is then a VGH_OP_CONV with cin = 32. */
 enum { VGH_OP_STEM = 0, VGH_OP_CONV = 1, VGH_OP_SPP = 2 };
 
 typedef struct {
@@ -98,8 +100,6 @@ typedef struct {
   int64_t n_weights;
   const float* bias_host;
   int64_t n_bias;
-  const float* stem_w_host;      /* [48][27] fp32 (ky,kx,c), already divided by 255 */
-  const float* stem_b_host;      /* [48] */
   int32_t reg_buf[3], flame_buf[3]; /* raw head output buffers per level (fp32) */
   int32_t keep_k;                /* capacity of survivors per image (keep_top_k, utils.py:166) */
 } vgh_net_desc;

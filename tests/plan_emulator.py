@@ -18,12 +18,14 @@ def apply_op(pk, op, m, bufs, images_u8=None, emulate_bf16=True):
     """Execute ONE plan op on the given NHWC float buffers (in place)."""
     P = pk.plan
     rnd = bf16_round if emulate_bf16 else (lambda t: t)
-    if op.kind == _lib.OP_STEM:
+    if op.kind == _lib.OP_STEM:  # im2col of the uint8 image: [B,S/2,S/2,32] = 27 taps (ky,kx,c) + 5 zeros
         x = images_u8.permute(0, 3, 1, 2).float()
-        w = torch.from_numpy(pk.stem_w).reshape(48, 3, 3, 3).permute(0, 3, 1, 2)
-        y = F.relu(F.conv2d(x, w, torch.from_numpy(pk.stem_b), stride=2, padding=1))
-        bufs[op.dst[0]][..., :48] = rnd(y.permute(0, 2, 3, 1))
-        bufs[op.dst[0]][..., 48:] = 0
+        cols = F.unfold(x, kernel_size=3, padding=1, stride=2)            # [B, c*9 + ky*3 + kx, L]
+        Bn, _, L = cols.shape
+        Ho = images_u8.shape[1] // 2
+        cols = cols.view(Bn, 3, 9, L).permute(0, 3, 2, 1).reshape(Bn, Ho, Ho, 27)   # -> (ky,kx,c) order
+        bufs[op.dst[0]][..., :27] = cols
+        bufs[op.dst[0]][..., 27:] = 0
     elif op.kind == _lib.OP_SPP:
         b = bufs[op.src[0]]
         C = op.src[2]

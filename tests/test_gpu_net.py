@@ -67,7 +67,8 @@ def test_end_to_end_vs_oracle_network_640():
     img = torch.randint(0, 256, (1, 640, 640, 3), dtype=torch.uint8)
     boxes, scores = eng.forward(img.cuda())
     dense = eng.dense_flame().cpu()
-    wq = {k: (v.to(torch.bfloat16).float() if k.endswith(".w") and not k.startswith("stem") else v) for k, v in w.items()}
+    wq = {k: (v.to(torch.bfloat16).float() if k.endswith(".w") else v) for k, v in w.items()}
+    wq["stem.w"] = (w["stem.w"] / 255.0).to(torch.bfloat16).float() * 255.0  # the packed stem weights carry the /255
     with torch.no_grad():
         ob, os_, of = no.DeployNet(wq, act_round=pe.bf16_round).forward(img.permute(0, 3, 1, 2).float() / 255)
     assert eng.A == 8400 and boxes.shape == (1, 8400, 4)

@@ -46,7 +46,8 @@ def test_plan_and_packing_reproduce_oracle():
     pk = arch.pack(arch.build_plan(S), w)
     torch.manual_seed(0)
     img = torch.randint(0, 256, (2, S, S, 3), dtype=torch.uint8)
-    wq = {k: (v.to(torch.bfloat16).float() if k.endswith(".w") and not k.startswith("stem") else v) for k, v in w.items()}
+    wq = {k: (v.to(torch.bfloat16).float() if k.endswith(".w") else v) for k, v in w.items()}
+    wq["stem.w"] = (w["stem.w"] / 255.0).to(torch.bfloat16).float() * 255.0  # the packed stem weights carry the /255
     taps = {}
     with torch.no_grad():
         no.DeployNet(wq).forward(img.permute(0, 3, 1, 2).float() / 255, taps)
