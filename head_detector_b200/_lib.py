@@ -30,6 +30,7 @@ class OpDesc(C.Structure):
         ("res_buf", C.c_int32), ("res_coff", C.c_int32), ("res_alpha", C.c_float),
         ("n_pad", C.c_int32), ("k_total", C.c_int32), ("block_n", C.c_int32),
         ("w_off", C.c_int64), ("b_off", C.c_int64),
+        ("lane", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

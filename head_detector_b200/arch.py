@@ -63,6 +63,7 @@ class Op:
     parts: List[Part] = field(default_factory=list)
     n_pad: int = 0
     label: str = ""
+    lane: int = 0  # independent branches of the graph run on separate lanes (CUDA streams / graph branches)
 
 
 class Plan:
@@ -74,6 +75,7 @@ class Plan:
         self.ops: List[Op] = []
         self.reg_buf: List[int] = []
         self.flame_buf: List[int] = []
+        self.lane = 0  # lane given to ops appended from now on
 
     # -- helpers
     def buf(self, name, res, C, fp32=0):
@@ -85,7 +87,7 @@ class Plan:
         rows = max(p.row + p.cout for p in parts) if not up else 4 * up_cout
         stored = cout if cout is not None else rows
         assert stored % 16 == 0, (label, stored)
-        self.ops.append(Op(_lib.OP_CONV, src, dst, stored, k, stride, relu, up, up_cout, res, parts, 0, label))
+        self.ops.append(Op(_lib.OP_CONV, src, dst, stored, k, stride, relu, up, up_cout, res, parts, 0, label, self.lane))
 
     def simple(self, name, src, dst, cout, k=1, stride=1, relu=1, res=None, cin_logical=None):
         cin = src[2] if cin_logical is None else cin_logical
@@ -153,10 +155,15 @@ def build_plan(image_size: int = 640) -> Plan:
         fuse = P.buf(name + ".fuse_in", R, 3 * out)
         P.conv(name + ".up", (inter_dst[0], inter_dst[1], out), (fuse, 0),
                [Part(name + ".up", 0, 4 * out, [(0, 0, out)], transposed=True)], relu=0, up=1, up_cout=out)
+        # the two skip branches only depend on backbone features: separate lanes let them fill the
+        # tails of the (much earlier) backbone kernels
+        P.lane = 13
         P.simple(name + ".skip1", (s1, 0, s1c), (fuse, out), out)
+        P.lane = 14
         s2r = P.buf(name + ".s2r", R * 2, out)
         P.simple(name + ".skip2_reduce", (s2, 0, s2c), (s2r, 0), out)
         P.simple(name + ".skip2_down", (s2r, 0, out), (fuse, 2 * out), out, k=3, stride=2)
+        P.lane = 0
         y = P.buf(name + ".y", R, out)
         P.simple(name + ".fuse", (fuse, 0, 3 * out), (y, 0), out)
         o = P.buf(out_name, R, out)
@@ -174,9 +181,12 @@ def build_plan(image_size: int = 640) -> Plan:
 
     for l, ((cin, bb, stride), feat) in enumerate(zip(HEADS, (p3, p4, p5)), start=1):
         h, R = f"head{l}", S // stride
+        lane_a, lane_b, lane_c, lane_d = 1 + 4 * (l - 1), 2 + 4 * (l - 1), 3 + 4 * (l - 1), 4 + 4 * (l - 1)
+        P.lane = lane_a
         st = P.buf(h + ".stems", R, bb + FLAME_INTER)
         P.conv(h + ".stems", (feat, 0, cin), (st, 0),
                [Part(h + ".bbox_stem", 0, bb, [(0, 0, cin)]), Part(h + ".pose_stem", bb, FLAME_INTER, [(0, 0, cin)])])
+        P.lane = lane_d   # box branch: cls|reg -> preds
         cr = P.buf(h + ".clsreg", R, 2 * bb)
         P.conv(h + ".cls|reg", (st, 0, bb), (cr, 0),
                [Part(h + ".cls_conv", 0, bb, [(0, 0, bb)]), Part(h + ".reg_conv", bb, bb, [(0, 0, bb)])], k=3)
@@ -184,6 +194,7 @@ def build_plan(image_size: int = 640) -> Plan:
         P.conv(h + ".preds", (cr, 0, 2 * bb), (reg, 0),
                [Part(h + ".reg_pred", 0, 68, [(bb, 0, bb)]), Part(h + ".cls_pred", 68, 1, [(0, 0, bb)])], relu=0, cout=REG_ROWS)
         P.reg_buf.append(reg)
+        P.lane = lane_a   # flame branch
         t_prev = P.buf(h + ".t0", R, 512)
         parts, row = [], 0
         for tower, inter, _ in TOWERS:
@@ -192,17 +203,22 @@ def build_plan(image_size: int = 640) -> Plan:
         P.conv(h + ".towers0", (st, bb, FLAME_INTER), (t_prev, 0), parts, k=3)
         for i in (1, 2):
             t_next = P.buf(f"{h}.t{i}", R, 512)
+            P.lane = lane_a
             P.simple(f"{h}.shape.{i}", (t_prev, 0, 256), (t_next, 0), 256, k=3)
+            P.lane = lane_b
             P.simple(f"{h}.expr.{i}", (t_prev, 256, 128), (t_next, 256), 128, k=3)
+            P.lane = lane_c
             P.conv(f"{h}.transf.{i}", (t_prev, 384, 128), (t_next, 384),
                    [Part(f"{h}.{tw}.{i}", 32 * q, 32, [(32 * q, 0, 32)]) for q, tw in enumerate(("rot", "jaw", "scale", "transl"))], k=3)
             t_prev = t_next
+        P.lane = lane_a
         fl = P.buf(h + ".flame_raw", R, FLAME_ROWS, fp32=1)
         col = {"shape": (0, 256), "expr": (256, 128), "rot": (384, 32), "jaw": (416, 32), "scale": (448, 32), "transl": (480, 32)}
         P.conv(h + ".flame_out", (t_prev, 0, 512), (fl, 0),
                [Part(f"{h}.{tw}.out", RAW_ROW_OFF[tw], oc, [(col[tw][0], 0, col[tw][1])]) for tw, _, oc in TOWERS],
                relu=0, cout=FLAME_ROWS)
         P.flame_buf.append(fl)
+    P.lane = 0
     return P
 
 

@@ -5,6 +5,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -99,6 +100,9 @@ struct vgh_detector {
   const float *ovr_boxes = nullptr, *ovr_scores = nullptr;
   cudaGraphExec_t graph = nullptr;
   cudaStream_t cap_stream = nullptr;  // capture needs a non-legacy stream; the graph then replays anywhere
+  std::vector<cudaStream_t> lane_streams;  // side streams for independent graph branches (lanes 1..)
+  std::vector<cudaEvent_t> op_events;
+  bool multi_lane = true;
   float g_conf = -1.f, g_iou = -1.f;
   int g_topk = -1;
   int launches = 0;
@@ -241,6 +245,8 @@ extern "C" void vgh_detector_destroy(vgh_detector* d) {
   if (!d) return;
   if (d->graph) cudaGraphExecDestroy(d->graph);
   if (d->cap_stream) cudaStreamDestroy(d->cap_stream);
+  for (cudaStream_t t : d->lane_streams) cudaStreamDestroy(t);
+  for (cudaEvent_t e : d->op_events) if (e) cudaEventDestroy(e);
   for (void* p : d->buf_ptr) cudaFree(p);
   void* ptrs[] = {d->weights, d->bias, d->input, d->boxes, d->scores, d->keep_boxes,
                   d->keep_scores, d->keep_idx, d->keep_cnt, d->offsets, d->head_img, d->params, d->head_xform,
@@ -266,6 +272,10 @@ extern "C" int vgh_detector_create(const vgh_net_desc* n, const vgh_flame* flame
   d->S = n->image_size;
   d->keep_k = n->keep_k > 0 ? n->keep_k : 100;
   d->flame = flame;
+  {
+    const char* e = getenv("VGGHEADS_B200_SINGLE_LANE");
+    d->multi_lane = !(e && e[0] == '1');
+  }
   int rc = 0;
   auto bail = [&](int code) { vgh_detector_destroy(d); return code; };
 
@@ -330,28 +340,92 @@ extern "C" int vgh_detector_create(const vgh_net_desc* n, const vgh_flame* flame
   return 0;
 }
 
-static int run_forward(vgh_detector* d, const uint8_t* images, cudaStream_t s, int* launches) {
-  for (OpRt& o : d->ops) {
-    int rc = 0;
-    switch (o.d.kind) {
-      case VGH_OP_STEM:
-        rc = stem_pack_launch(images, static_cast<__nv_bfloat16*>(d->buf_ptr[o.d.out_buf]), d->B, d->S, s);
-        if (rc) return fail(5, "stem launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-        break;
-      case VGH_OP_CONV:
-        rc = conv_launch(o.L, o.bk, s);
-        if (rc) return fail(5, "%s", conv_last_error());
-        break;
-      case VGH_OP_SPP: {
-        const vgh_buf_desc& b = d->bufs[o.d.in_buf];
-        rc = spp_pool_launch(static_cast<__nv_bfloat16*>(d->buf_ptr[o.d.in_buf]), d->B, b.H, b.W, o.d.cin, s);
-        if (rc) return fail(5, "spp launch failed");
-        break;
-      }
-      default:
-        return fail(5, "unknown op kind %d", o.d.kind);
+static int launch_op(vgh_detector* d, OpRt& o, const uint8_t* images, cudaStream_t s) {
+  int rc = 0;
+  switch (o.d.kind) {
+    case VGH_OP_STEM:
+      rc = stem_pack_launch(images, static_cast<__nv_bfloat16*>(d->buf_ptr[o.d.out_buf]), d->B, d->S, s);
+      if (rc) return fail(5, "stem launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+      break;
+    case VGH_OP_CONV:
+      rc = conv_launch(o.L, o.bk, s);
+      if (rc) return fail(5, "%s", conv_last_error());
+      break;
+    case VGH_OP_SPP: {
+      const vgh_buf_desc& b = d->bufs[o.d.in_buf];
+      rc = spp_pool_launch(static_cast<__nv_bfloat16*>(d->buf_ptr[o.d.in_buf]), d->B, b.H, b.W, o.d.cin, s);
+      if (rc) return fail(5, "spp launch failed");
+      break;
     }
+    default:
+      return fail(5, "unknown op kind %d", o.d.kind);
+  }
+  return 0;
+}
+
+// Executes the plan on `s` (lane 0) plus side streams for the other lanes.  Independent branches of
+// the graph (the three head levels, the parallel tower chains) run on their own lanes so that the
+// pipeline fill/drain of one kernel is covered by CTAs of another; cross-lane ordering comes from
+// buffer-level dependency tracking (RAW / WAR / WAW per activation buffer), expressed as events -
+// which CUDA-graph capture turns into graph edges.
+static int run_forward(vgh_detector* d, const uint8_t* images, cudaStream_t s, int* launches) {
+  const int n_ops = static_cast<int>(d->ops.size());
+  const int n_bufs = static_cast<int>(d->bufs.size());
+  if (d->op_events.size() < static_cast<size_t>(n_ops)) {
+    d->op_events.resize(n_ops, nullptr);
+    for (auto& e : d->op_events) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  int max_lane = 0;
+  for (const OpRt& o : d->ops) max_lane = o.d.lane > max_lane ? o.d.lane : max_lane;
+  if (!d->multi_lane) max_lane = 0;
+  while (static_cast<int>(d->lane_streams.size()) < max_lane) {
+    cudaStream_t t;
+    CUDA_OK(cudaStreamCreateWithFlags(&t, cudaStreamNonBlocking));
+    d->lane_streams.push_back(t);
+  }
+  auto stream_of = [&](int lane) { return lane == 0 ? s : d->lane_streams[lane - 1]; };
+  const int L = max_lane + 1;
+  std::vector<int> last_w(static_cast<size_t>(n_bufs) * L, -1), last_r(static_cast<size_t>(n_bufs) * L, -1);
+  std::vector<char> recorded(n_ops, 0);
+  std::vector<int> last_op_on_lane(L, -1);
+  auto depend = [&](int lane, int op_j) -> int {  // lane must wait for op_j (which ran on another lane)
+    if (op_j < 0) return 0;
+    const int lj = d->multi_lane ? d->ops[op_j].d.lane : 0;
+    if (lj == lane) return 0;
+    if (!recorded[op_j]) {
+      CUDA_OK(cudaEventRecord(d->op_events[op_j], stream_of(lj)));
+      recorded[op_j] = 1;
+    }
+    CUDA_OK(cudaStreamWaitEvent(stream_of(lane), d->op_events[op_j], 0));
+    return 0;
+  };
+  for (int i = 0; i < n_ops; ++i) {
+    OpRt& o = d->ops[i];
+    const int lane = d->multi_lane ? o.d.lane : 0;
+    if (L > 1) {
+      int reads[2] = {o.d.kind == VGH_OP_STEM ? -1 : o.d.in_buf, o.d.res_buf};
+      for (int b : reads) {
+        if (b < 0) continue;
+        for (int l2 = 0; l2 < L; ++l2) { int rc = depend(lane, last_w[b * L + l2]); if (rc) return rc; }
+      }
+      const int wb = o.d.kind == VGH_OP_SPP ? o.d.in_buf : o.d.out_buf;
+      for (int l2 = 0; l2 < L; ++l2) {
+        int rc = depend(lane, last_w[wb * L + l2]);
+        if (!rc) rc = depend(lane, last_r[wb * L + l2]);
+        if (rc) return rc;
+      }
+      for (int b : reads)
+        if (b >= 0) last_r[b * L + lane] = i;
+      last_w[wb * L + lane] = i;
+    }
+    int rc = launch_op(d, o, images, stream_of(lane));
+    if (rc) return rc;
+    last_op_on_lane[lane] = i;
     if (launches) ++*launches;
+  }
+  for (int l2 = 1; l2 < L; ++l2) {  // join every side lane back into lane 0
+    int rc = depend(0, last_op_on_lane[l2]);
+    if (rc) return rc;
   }
   if (box_decode_launch(d->lv, d->boxes, d->scores, d->B, d->A, s)) return fail(5, "box decode launch failed");
   if (launches) ++*launches;

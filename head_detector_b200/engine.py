@@ -34,6 +34,7 @@ class Engine:
             o.out_buf, o.out_coff = op.dst
             o.cout, o.ksize, o.stride, o.relu, o.up, o.up_cout = op.cout, op.k, op.stride, op.relu, op.up, op.up_cout
             o.res_buf, o.res_coff = (op.res[0], op.res[1]) if op.res is not None else (-1, 0)
+            o.lane = op.lane
             if m:
                 o.res_alpha, o.n_pad, o.k_total, o.block_n = m["alpha"], m["n_pad"], m["k_total"], m["block_n"]
                 o.w_off, o.b_off = m["w_off"], m["b_off"]

@@ -89,6 +89,7 @@ typedef struct {
   float res_alpha;
   int32_t n_pad, k_total, block_n;   /* packed weight matrix [n_pad][k_total] bf16, UMMA N */
   int64_t w_off, b_off;              /* element offsets into the weight / bias blobs */
+  int32_t lane, reserved;            /* independent graph branches run on separate lanes (streams); 0 = main */
 } vgh_op_desc;
 
 typedef struct {
