@@ -43,6 +43,25 @@ def _peaks():
     return {"tflops": 1400.0, "hbm": 6650.0, "src": "fallback (B200_PROFILING.md)"}
 
 
+def ncu_conv_traffic():
+    """DRAM bytes moved by the conv_igemm launches of ONE step (dram__bytes_read+write summed over the
+    launches) from the committed ncu launch list of the same workload; None if the file is absent."""
+    import csv
+
+    path = os.path.join(ROOT, "profiles", "r1_ncu_launches_metrics.csv")
+    if not os.path.exists(path):
+        return None
+    tot = 0.0
+    with open(path) as f:
+        rows = csv.DictReader(l for l in f if l.startswith('"'))
+        for r in rows:
+            if "conv_igemm" in r["Kernel Name"] and r["Metric Name"] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                v = float(r["Metric Value"].replace(",", ""))
+                unit = r["Metric Unit"].lower()
+                tot += v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1)
+    return tot or None
+
+
 class ClockSampler:
     """nvidia-smi clock / throttle sampling DURING the timed region (profiling recipe's clocks line)."""
 
@@ -256,7 +275,8 @@ def run_ours(args, rank, world, local_rank):
         pk = _peaks()
         ach = conv_flops / (conv_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "conv_igemm_kernel (125 launches/step)", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s",
-                "frac": ach / pk["tflops"], "peak_source": pk["src"], "traffic": None,
+                "frac": ach / pk["tflops"], "peak_source": pk["src"], "traffic": ncu_conv_traffic(),
+                "traffic_note": "DRAM bytes of all conv_igemm launches of one step (profiles/r1_ncu_launches_metrics.csv); algorithmic activation bytes are ~13 GB/step",
                 "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_ms / all_ms,
                 "algorithmic_flops_per_step": conv_flops}
         if world == 1:
