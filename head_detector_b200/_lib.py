@@ -64,6 +64,8 @@ _SIGS = {
     "vgh_detector_read_buffer": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
     "vgh_detector_run_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "vgh_detector_submit_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int]),
+    "vgh_detector_collect_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "vgh_detector_run_device": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_void_p]),
     "vgh_detector_set_override": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "vgh_detector_profile": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),

@@ -134,19 +134,35 @@ int spp_pool_launch(__nv_bfloat16* buf, int B, int H, int W, int C, cudaStream_t
 
 // ---------------------------------------------------------------------------------------- box decode
 // yolo_head_ndfl_heads.py:143-144,164-165: DFL softmax expectation, sigmoid, distance2bbox * stride.
-__global__ void __launch_bounds__(256) box_decode_kernel(const DecodeLevels lv, float* __restrict__ boxes,
-                                                         float* __restrict__ scores, int B, int A) {
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= static_cast<long long>(B) * A) return;
-  const int a = static_cast<int>(idx % A);
-  const int b = static_cast<int>(idx / A);
+// CTA = 128 consecutive anchors of one image and level: the 128 x reg_cstride raw rows are staged in
+// shared memory with coalesced 16-byte loads (row pitch +1 float: conflict-free per-thread reads).
+__global__ void __launch_bounds__(128) box_decode_kernel(const DecodeLevels lv, float* __restrict__ boxes,
+                                                         float* __restrict__ scores, int B, int A, int blocks_l0,
+                                                         int blocks_l1, int blocks_per_img) {
+  extern __shared__ float rows[];  // [128][cs + 1]
+  const int b = blockIdx.x / blocks_per_img;
+  int blk = blockIdx.x - b * blocks_per_img;
   int l = 0;
-  while (l < 2 && a >= lv.a_off[l + 1]) ++l;
-  const int pix = a - lv.a_off[l];
+  if (blk >= blocks_l0) { blk -= blocks_l0; l = 1; if (blk >= blocks_l1) { blk -= blocks_l1; l = 2; } }
+  const int cs = lv.reg_cstride, pitch = cs + 1;
+  const int pix0 = blk * 128;
+  const int n_here = min(128, lv.hw[l] - pix0);
+  const float* src = lv.reg[l] + (static_cast<size_t>(b) * lv.hw[l] + pix0) * cs;
+  const int vec_per_row = cs >> 2;
+  for (int i = threadIdx.x; i < n_here * vec_per_row; i += blockDim.x) {
+    const int r = i / vec_per_row, c4 = i - r * vec_per_row;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+    float* dst = rows + r * pitch + c4 * 4;
+    dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+  }
+  __syncthreads();
+  if (threadIdx.x >= n_here) return;
+  const int pix = pix0 + threadIdx.x;
+  const int a = lv.a_off[l] + pix;
   const int W = lv.W[l];
   const float s = lv.stride[l];
   const float ax = static_cast<float>(pix % W) + 0.5f, ay = static_cast<float>(pix / W) + 0.5f;
-  const float* r = lv.reg[l] + (static_cast<size_t>(b) * lv.hw[l] + pix) * lv.reg_cstride;
+  const float* r = rows + threadIdx.x * pitch;
   float d[4];
 #pragma unroll
   for (int side = 0; side < 4; ++side) {
@@ -164,14 +180,16 @@ __global__ void __launch_bounds__(256) box_decode_kernel(const DecodeLevels lv, 
     d[side] = ex / sum;
   }
   const float logit = r[68];
-  float4 o = make_float4((ax - d[0]) * s, (ay - d[1]) * s, (ax + d[2]) * s, (ay + d[3]) * s);
-  reinterpret_cast<float4*>(boxes)[idx] = o;
+  const size_t idx = static_cast<size_t>(b) * A + a;
+  reinterpret_cast<float4*>(boxes)[idx] = make_float4((ax - d[0]) * s, (ay - d[1]) * s, (ax + d[2]) * s, (ay + d[3]) * s);
   scores[idx] = 1.f / (1.f + expf(-logit));
 }
 
 int box_decode_launch(const DecodeLevels& lv, float* boxes, float* scores, int B, int A, cudaStream_t stream) {
-  const long long total = static_cast<long long>(B) * A;
-  box_decode_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, stream>>>(lv, boxes, scores, B, A);
+  const int b0 = (lv.hw[0] + 127) / 128, b1 = (lv.hw[1] + 127) / 128, b2 = (lv.hw[2] + 127) / 128;
+  const int per_img = b0 + b1 + b2;
+  const size_t smem = 128 * (lv.reg_cstride + 1) * sizeof(float);
+  box_decode_kernel<<<B * per_img, 128, smem, stream>>>(lv, boxes, scores, B, A, b0, b1, per_img);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
@@ -269,6 +287,26 @@ int flame_gather_launch(const DecodeLevels& lv, const int* keep_idx, const int* 
   head_offsets_kernel<<<1, 1024, 0, stream>>>(keep_cnt, B, offsets, total);
   flame_gather_kernel<<<dim3(keep_k, B), 128, 0, stream>>>(lv, keep_idx, keep_cnt, offsets, keep_k, img_xform, params,
                                                            head_xform, head_img);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+// ---------------------------------------------------------------------------------------- result staging
+// Copies the first *count_ptr rows (row_floats floats each) of src to dst; the count lives on the device.
+__global__ void __launch_bounds__(256) copy_rows_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                        const int* __restrict__ count_ptr, int row_floats, int max_rows) {
+  const int rows = min(*count_ptr, max_rows);
+  const size_t n = static_cast<size_t>(rows) * row_floats;
+  const size_t n4 = n >> 2;
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    d4[i] = s4[i];
+  for (size_t i = (n4 << 2) + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    dst[i] = src[i];
+}
+
+int copy_rows_launch(const float* src, float* dst, const int* count_ptr, int row_floats, int max_rows, cudaStream_t stream) {
+  copy_rows_kernel<<<592, 256, 0, stream>>>(src, dst, count_ptr, row_floats, max_rows);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

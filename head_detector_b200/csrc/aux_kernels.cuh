@@ -24,4 +24,5 @@ int flame_dense_launch(const DecodeLevels& lv, float* out, int B, int A, cudaStr
 int flame_gather_launch(const DecodeLevels& lv, const int* keep_idx, const int* keep_cnt, int B, int keep_k,
                         const float* img_xform, int* offsets, int* total, float* params, float* head_xform,
                         int* head_img, cudaStream_t stream);
+int copy_rows_launch(const float* src, float* dst, const int* count_ptr, int row_floats, int max_rows, cudaStream_t stream);
 }  // namespace vgh

@@ -10,7 +10,7 @@
 // is rounded once to fp32, and the remaining ops (R*v, *scale, +t, -pad, /scale) are done in fp32
 // in the reference's operation order with non-contracted intrinsics so that roundings coincide.
 //
-// Work decomposition: CTA = 128 vertices x (8*HG heads).  Each thread owns one vertex (3 coords) for
+// Work decomposition: item = 128 vertices x (8*HG heads), persistent CTAs walk the items.  Each thread owns one vertex (3 coords) for
 // 8 heads = 24 fp64 accumulators.  The shape basis slab of the CTA's 128 vertices streams through a
 // double-buffered cp.async pipeline (8 coefficients per stage) and is shared by the HG head groups;
 // betas live in shared memory as fp64 and are read as broadcast 128-bit loads.
@@ -115,10 +115,14 @@ template <int HG>
 __global__ void __launch_bounds__(kTileV* HG) flame_decode_kernel(const FlameArgs a) {
   constexpr int kHeads = kHPT * HG;
   const int n_heads = a.n_dev ? min(*a.n_dev, a.n) : a.n;
-  const int head0 = blockIdx.y * kHeads;
-  if (head0 >= n_heads) return;
-  const int v0 = blockIdx.x * kTileV;
+  // work items = (vertex tile, head group); CTAs walk them with a grid stride so that the device-side
+  // head count decides the amount of work, not the (capacity-sized) launch
+  constexpr int kVTiles = kVPad / kTileV;
+  const int n_items = kVTiles * ((n_heads + kHeads - 1) / kHeads);
   const int tid = threadIdx.x;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+  const int head0 = (item / kVTiles) * kHeads;
+  const int v0 = (item % kVTiles) * kTileV;
   const int vl = tid % kTileV;
   const int grp = tid / kTileV;
   const int lb = a.ns + a.ne;          // live blendshape coefficients
@@ -153,7 +157,7 @@ __global__ void __launch_bounds__(kTileV* HG) flame_decode_kernel(const FlameArg
       t[0] = p[409]; t[1] = p[410]; t[2] = p[411];
       sc = fmaxf(p[412], 1e-8f);
       if (a.xform) { xf[0] = a.xform[hg * 3]; xf[1] = a.xform[hg * 3 + 1]; xf[2] = a.xform[hg * 3 + 2]; }
-      if (a.rot && blockIdx.x == 0)
+      if (a.rot && v0 == 0)
         for (int i = 0; i < 9; ++i) a.rot[static_cast<size_t>(hg) * 9 + i] = R[i];
     }
     for (int i = 0; i < 9; ++i) {
@@ -254,7 +258,7 @@ __global__ void __launch_bounds__(kTileV* HG) flame_decode_kernel(const FlameArg
 
   // ---- epilogue: skinning + rigid transform, per head
   const int v = v0 + vl;
-  if (v >= kV) return;
+  if (v < kV) {
   const double wi = a.c.wI[v], w2 = a.c.w2[v];
 #pragma unroll
   for (int h = 0; h < kHPT; ++h) {
@@ -287,6 +291,9 @@ __global__ void __launch_bounds__(kTileV* HG) flame_decode_kernel(const FlameArg
     a.proj[o + 1] = __fdiv_rn(out[1], st[6]);
     a.proj[o + 2] = __fdiv_rn(out[2], st[6]);
   }
+  }  // v < kV
+  __syncthreads();  // shared memory is reused by the next work item
+  }  // item loop
 }
 
 // ------------------------------------------------------------------------------------------- host
@@ -380,7 +387,14 @@ static int launch_flame(const FlameArgs& a, cudaStream_t stream, char* err, size
     }
     configured = smem;
   }
-  dim3 grid(kVPad / kTileV, (a.n + heads - 1) / heads);
+  int dev = 0, sms = 148, per_sm = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flame_decode_kernel<HG>, kTileV * HG, smem);
+  if (per_sm < 1) per_sm = 1;
+  const int max_items = (kVPad / kTileV) * ((a.n + heads - 1) / heads);
+  int grid = sms * per_sm;
+  if (grid > max_items) grid = max_items;
   flame_decode_kernel<HG><<<grid, kTileV * HG, smem, stream>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -402,7 +416,9 @@ int flame_decode_launch(const FlameModel* m, const float* params, int n, const i
   a.c = m->dev;
   a.params = params; a.xform = xform; a.n_dev = n_dev; a.verts = verts; a.rot = rot; a.proj = proj;
   a.n = n; a.ns = ns; a.ne = ne;
-  if (n > 16) return launch_flame<4>(a, stream, err, errlen);
+  // 16-head items: small enough to balance over the SMs whatever the (device-side) head count is,
+  // large enough to amortise the basis stream; tiny batches use 8-head items
+  if (n > 8) return launch_flame<2>(a, stream, err, errlen);
   return launch_flame<1>(a, stream, err, errlen);
 }
 

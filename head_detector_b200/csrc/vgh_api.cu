@@ -100,6 +100,16 @@ struct vgh_detector {
   const float *ovr_boxes = nullptr, *ovr_scores = nullptr;
   cudaGraphExec_t graph = nullptr;
   cudaStream_t cap_stream = nullptr;  // capture needs a non-legacy stream; the graph then replays anywhere
+  // two-deep host pipeline (vgh_detector_submit_host / collect_host)
+  struct Slot {
+    uint8_t* in_dev = nullptr;
+    float *params = nullptr, *verts = nullptr, *kboxes = nullptr, *kscores = nullptr;
+    int *cnt = nullptr, *total = nullptr;
+    cudaEvent_t h2d_done = nullptr, in_consumed = nullptr, compute_done = nullptr, d2h_done = nullptr;
+    bool busy = false;
+  } slots[2];
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr, pipe_stream = nullptr;
+  int submit_idx = 0, collect_idx = 0;
   std::vector<cudaStream_t> lane_streams;  // side streams for independent graph branches (lanes 1..)
   std::vector<cudaEvent_t> op_events;
   bool multi_lane = true;
@@ -123,14 +133,14 @@ static void pick_tile(int Ho, int Wo, int& tw, int& th) {
 }
 
 // swapped mode: tile of up to 256 pixels whose pixel count is a multiple of 16 (it is the UMMA N)
-static void pick_tile_swap(int Ho, int Wo, int& tw, int& th) {
+static void pick_tile_swap(int Ho, int Wo, int& tw, int& th, int max_px = 256) {
   double best = -1.0;
   tw = 16; th = 1;
-  for (int h = 1; h <= 256 && h <= Ho; ++h) {
-    for (int w = (256 / h < Wo ? 256 / h : Wo); w >= 1; --w) {
+  for (int h = 1; h <= max_px && h <= Ho; ++h) {
+    for (int w = (max_px / h < Wo ? max_px / h : Wo); w >= 1; --w) {
       if ((w * h) % 16) continue;
       const int tx = (Wo + w - 1) / w, ty = (Ho + h - 1) / h;
-      const double eff = static_cast<double>(Ho) * Wo / (static_cast<double>(tx) * ty * 256.0);
+      const double eff = static_cast<double>(Ho) * Wo / (static_cast<double>(tx) * ty * max_px);
       if (eff > best + 1e-9) { best = eff; tw = w; th = h; }
       break;  // widest admissible w for this h only
     }
@@ -245,6 +255,13 @@ extern "C" void vgh_detector_destroy(vgh_detector* d) {
   if (!d) return;
   if (d->graph) cudaGraphExecDestroy(d->graph);
   if (d->cap_stream) cudaStreamDestroy(d->cap_stream);
+  for (auto& sl : d->slots) {
+    void* sp[] = {sl.in_dev, sl.params, sl.verts, sl.kboxes, sl.kscores, sl.cnt, sl.total};
+    for (void* q : sp) cudaFree(q);
+    cudaEvent_t ev[] = {sl.h2d_done, sl.in_consumed, sl.compute_done, sl.d2h_done};
+    for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e);
+  }
+  for (cudaStream_t t : {d->h2d_stream, d->d2h_stream, d->pipe_stream}) if (t) cudaStreamDestroy(t);
   for (cudaStream_t t : d->lane_streams) cudaStreamDestroy(t);
   for (cudaEvent_t e : d->op_events) if (e) cudaEventDestroy(e);
   for (void* p : d->buf_ptr) cudaFree(p);
@@ -467,26 +484,29 @@ extern "C" int vgh_detector_autotune(vgh_detector* d, int iters, void* stream) {
   for (OpRt& o : d->ops) {
     if (o.d.kind != VGH_OP_CONV) continue;
     float best = 1e30f;
-    int best_mt = 0, best_st = 0, best_swap = 0;
+    int best_mt = 0, best_st = 0, best_swap = 0, best_tw = 0, best_th = 0;
     const int bn = o.L.block_n;
     if (swap_eligible(o.d, d->bufs[o.d.out_buf])) {
-      OpRt t = o;
-      t.cfg_swap = 1; t.cfg_mt = 0; t.cfg_stages = 0; t.cfg_tw = 0; t.cfg_th = 0;
-      if (!build_conv(d, t) && !conv_launch(t.L, t.bk, s)) {
+      for (int max_px : {256, 192, 128}) {  // pixel-tile size trades MMA width against pipeline depth
+        OpRt t = o;
+        t.cfg_swap = 1; t.cfg_mt = 0; t.cfg_stages = 0;
+        pick_tile_swap(o.L.Ho, o.L.Wo, t.cfg_tw, t.cfg_th, max_px);
+        if (max_px != 256 && t.cfg_tw * t.cfg_th > max_px) continue;
+        if (build_conv(d, t) || conv_launch(t.L, t.bk, s)) continue;
         cudaEventRecord(e0, s);
         for (int i = 0; i < iters; ++i) conv_launch(t.L, t.bk, s);
         cudaEventRecord(e1, s);
         if (cudaStreamSynchronize(s) != cudaSuccess) return fail(7, "autotune (swap) launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
-        best = ms; best_swap = 1; best_mt = 1; best_st = 0;
+        if (ms < best) { best = ms; best_swap = 1; best_mt = 1; best_st = 0; best_tw = t.cfg_tw; best_th = t.cfg_th; }
       }
     }
     for (int mt : {1, 2, 4}) {
       if (mt * bn > 512) continue;
       for (int variant = 0; variant < 2; ++variant) {
         OpRt t = o;
-        t.cfg_swap = 0;
+        t.cfg_swap = 0; t.cfg_tw = 0; t.cfg_th = 0;
         t.cfg_mt = mt;
         const int stage_bytes = (128 * mt + bn) * t.bk * 2;
         int st = (variant == 0 ? 200 * 1024 : 100 * 1024) / stage_bytes;  // 1 CTA/SM deep vs 2 CTAs/SM
@@ -507,6 +527,8 @@ extern "C" int vgh_detector_autotune(vgh_detector* d, int iters, void* stream) {
     }
     if (best_mt) {
       o.cfg_swap = best_swap;
+      o.cfg_tw = best_swap ? best_tw : 0;
+      o.cfg_th = best_swap ? best_th : 0;
       o.cfg_mt = best_mt;
       o.cfg_stages = best_st;
       int rc = build_conv(d, o);
@@ -688,5 +710,88 @@ extern "C" int vgh_detector_run_host(vgh_detector* d, const uint8_t* images_host
     if (verts_host) CUDA_OK(cudaMemcpyAsync(verts_host, d->verts, (size_t)n * VGH_NUM_VERTS * 12, cudaMemcpyDeviceToHost, s));
     CUDA_OK(cudaStreamSynchronize(s));
   }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ host pipeline
+// Two-deep software pipeline over HOST buffers: while step i computes, the images of step i+1 are
+// uploaded and the results of step i-1 are downloaded (separate copy streams, double-buffered staging
+// on the device).  Every step still performs its own H2D and D2H copies; they just overlap compute.
+static int ensure_pipeline(vgh_detector* d) {
+  if (d->pipe_stream) return 0;
+  CUDA_OK(cudaStreamCreateWithFlags(&d->pipe_stream, cudaStreamNonBlocking));
+  CUDA_OK(cudaStreamCreateWithFlags(&d->h2d_stream, cudaStreamNonBlocking));
+  CUDA_OK(cudaStreamCreateWithFlags(&d->d2h_stream, cudaStreamNonBlocking));
+  const size_t B = d->B, K = d->keep_k, cap = B * K;
+  for (auto& sl : d->slots) {
+    if (dmalloc(&sl.in_dev, B * d->S * d->S * 3) != cudaSuccess || dmalloc(&sl.params, cap * VGH_NUM_PARAMS) != cudaSuccess ||
+        dmalloc(&sl.verts, cap * VGH_NUM_VERTS * 3) != cudaSuccess || dmalloc(&sl.kboxes, cap * 4) != cudaSuccess ||
+        dmalloc(&sl.kscores, cap) != cudaSuccess || dmalloc(&sl.cnt, B) != cudaSuccess || dmalloc(&sl.total, 1) != cudaSuccess)
+      return fail(4, "pipeline staging allocation failed");
+    for (cudaEvent_t* e : {&sl.h2d_done, &sl.in_consumed, &sl.compute_done, &sl.d2h_done})
+      CUDA_OK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  }
+  return 0;
+}
+
+extern "C" int vgh_detector_submit_host(vgh_detector* d, const uint8_t* images_host, float conf_thr, float iou_thr, int top_k) {
+  if (!d || !images_host) return fail(1, "null argument");
+  int rc = ensure_pipeline(d);
+  if (rc) return rc;
+  cudaStream_t s = d->pipe_stream;
+  rc = ensure_graph(d, conf_thr, iou_thr, top_k, s);
+  if (rc) return rc;
+  vgh_detector::Slot& sl = d->slots[d->submit_idx & 1];
+  if (sl.busy) return fail(8, "pipeline full: collect a result before submitting a third step");
+  const size_t B = d->B, K = d->keep_k;
+  // upload (copy stream); the slot's device image was last read by the D2D of its previous use
+  CUDA_OK(cudaStreamWaitEvent(d->h2d_stream, sl.in_consumed, 0));
+  CUDA_OK(cudaMemcpyAsync(sl.in_dev, images_host, B * d->S * d->S * 3, cudaMemcpyHostToDevice, d->h2d_stream));
+  CUDA_OK(cudaEventRecord(sl.h2d_done, d->h2d_stream));
+  // compute
+  CUDA_OK(cudaStreamWaitEvent(s, sl.h2d_done, 0));
+  CUDA_OK(cudaMemcpyAsync(d->input, sl.in_dev, B * d->S * d->S * 3, cudaMemcpyDeviceToDevice, s));
+  CUDA_OK(cudaEventRecord(sl.in_consumed, s));
+  CUDA_OK(cudaGraphLaunch(d->graph, s));
+  // stage the results of this step so that the next step may overwrite the live buffers
+  CUDA_OK(cudaStreamWaitEvent(s, sl.d2h_done, 0));
+  CUDA_OK(cudaMemcpyAsync(sl.cnt, d->keep_cnt, B * 4, cudaMemcpyDeviceToDevice, s));
+  CUDA_OK(cudaMemcpyAsync(sl.total, d->offsets + B, 4, cudaMemcpyDeviceToDevice, s));
+  CUDA_OK(cudaMemcpyAsync(sl.kboxes, d->keep_boxes, B * K * 16, cudaMemcpyDeviceToDevice, s));
+  CUDA_OK(cudaMemcpyAsync(sl.kscores, d->keep_scores, B * K * 4, cudaMemcpyDeviceToDevice, s));
+  if (copy_rows_launch(d->params, sl.params, d->offsets + B, VGH_NUM_PARAMS, (int)(B * K), s) ||
+      copy_rows_launch(d->verts, sl.verts, d->offsets + B, VGH_NUM_VERTS * 3, (int)(B * K), s))
+    return fail(5, "result staging launch failed");
+  CUDA_OK(cudaEventRecord(sl.compute_done, s));
+  sl.busy = true;
+  ++d->submit_idx;
+  return 0;
+}
+
+extern "C" int vgh_detector_collect_host(vgh_detector* d, int32_t* keep_cnt_host, float* keep_boxes_host,
+                                         float* keep_scores_host, float* params_host, float* verts_host, int max_heads,
+                                         int32_t* total_heads) {
+  if (!d || !keep_cnt_host || !total_heads) return fail(1, "null argument");
+  if (!d->pipe_stream) return fail(8, "nothing submitted");
+  vgh_detector::Slot& sl = d->slots[d->collect_idx & 1];
+  if (!sl.busy) return fail(8, "nothing to collect");
+  cudaStream_t c = d->d2h_stream;
+  const size_t B = d->B, K = d->keep_k;
+  CUDA_OK(cudaStreamWaitEvent(c, sl.compute_done, 0));
+  CUDA_OK(cudaMemcpyAsync(keep_cnt_host, sl.cnt, B * 4, cudaMemcpyDeviceToHost, c));
+  CUDA_OK(cudaMemcpyAsync(total_heads, sl.total, 4, cudaMemcpyDeviceToHost, c));
+  if (keep_boxes_host) CUDA_OK(cudaMemcpyAsync(keep_boxes_host, sl.kboxes, B * K * 16, cudaMemcpyDeviceToHost, c));
+  if (keep_scores_host) CUDA_OK(cudaMemcpyAsync(keep_scores_host, sl.kscores, B * K * 4, cudaMemcpyDeviceToHost, c));
+  CUDA_OK(cudaStreamSynchronize(c));
+  int n = *total_heads;
+  if (n > max_heads) n = max_heads;
+  if (n > 0) {
+    if (params_host) CUDA_OK(cudaMemcpyAsync(params_host, sl.params, (size_t)n * VGH_NUM_PARAMS * 4, cudaMemcpyDeviceToHost, c));
+    if (verts_host) CUDA_OK(cudaMemcpyAsync(verts_host, sl.verts, (size_t)n * VGH_NUM_VERTS * 12, cudaMemcpyDeviceToHost, c));
+  }
+  CUDA_OK(cudaEventRecord(sl.d2h_done, c));
+  CUDA_OK(cudaStreamSynchronize(c));
+  sl.busy = false;
+  ++d->collect_idx;
   return 0;
 }

@@ -137,6 +137,17 @@ class Engine:
             out["verts"].data_ptr(), out["verts"].shape[0], total.data_ptr(), _lib.stream_ptr()), "run_host")
         return int(total[0])
 
+    def submit_host(self, images_host: torch.Tensor, conf=0.5, iou=0.5, top_k=1000):
+        """Pipelined end-to-end: enqueue upload + compute + result staging of one batch (max 2 in flight)."""
+        _lib.check(_lib.lib().vgh_detector_submit_host(self._h, images_host.data_ptr(), conf, iou, top_k), "submit_host")
+
+    def collect_host(self, out: dict):
+        """Download the oldest outstanding batch into `out` (see alloc_host_outputs); returns total heads."""
+        _lib.check(_lib.lib().vgh_detector_collect_host(
+            self._h, out["keep_cnt"].data_ptr(), out["keep_boxes"].data_ptr(), out["keep_scores"].data_ptr(), out["params"].data_ptr(),
+            out["verts"].data_ptr(), out["verts"].shape[0], out["total"].data_ptr()), "collect_host")
+        return int(out["total"][0])
+
     def alloc_host_outputs(self, max_heads: int):
         pin = dict(pin_memory=True)
         return {

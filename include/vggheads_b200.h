@@ -145,6 +145,14 @@ int vgh_detector_run_host(vgh_detector* d, const uint8_t* images_host, const flo
                           float iou_thr, int top_k, int32_t* keep_cnt_host, float* keep_boxes_host,
                           float* keep_scores_host, float* params_host, float* verts_host, int max_heads,
                           int32_t* total_heads, void* stream);
+/* Two-deep pipelined form of vgh_detector_run_host for streams of batches: submit() enqueues the H2D
+ * upload (own copy stream), the graph replay and the staging of the results; collect() downloads the
+ * results of the OLDEST outstanding submission (own copy stream) and blocks until they are on the
+ * host.  At most two submissions may be outstanding.  Each step still does its own H2D and D2H; they
+ * overlap the compute of the neighbouring steps.  Host buffers should be pinned. */
+int vgh_detector_submit_host(vgh_detector* d, const uint8_t* images_host, float conf_thr, float iou_thr, int top_k);
+int vgh_detector_collect_host(vgh_detector* d, int32_t* keep_cnt_host, float* keep_boxes_host, float* keep_scores_host,
+                              float* params_host, float* verts_host, int max_heads, int32_t* total_heads);
 /* Same device work (graph replay) with inputs already resident in the internal staging buffer and
  * results left on the device - the kernel-only timing path. */
 int vgh_detector_run_device(vgh_detector* d, float conf_thr, float iou_thr, int top_k, void* stream);
