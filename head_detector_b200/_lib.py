@@ -66,6 +66,9 @@ _SIGS = {
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "vgh_detector_submit_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int]),
     "vgh_detector_collect_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "vgh_detector_submit_device": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p]),
+    "vgh_detector_release_slot": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "vgh_detector_slot_output": (C.c_void_p, [C.c_void_p, C.c_int, C.c_int]),
     "vgh_detector_run_device": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_void_p]),
     "vgh_detector_set_override": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "vgh_detector_profile": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),

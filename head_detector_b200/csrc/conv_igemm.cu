@@ -39,20 +39,35 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  // Tiles: per image tiles_x * tiles_y rectangles of th rows.  When the map height is not a multiple of
+  // th (p.tail_rows > 0), tiles_y counts only the FULL row groups and the left-over rows of
+  // p.tail_imgs consecutive images are packed into one extra tile (4-D box [BK, tw, tail_rows,
+  // tail_imgs]), which removes the mostly-empty last tile of every image (wave quantisation).
   const int tiles_per_img = p.tiles_x * p.tiles_y;
-  const int total_tiles = tiles_per_img * p.B;
-  auto tile_coords = [&](int t, int& b_img, int& h0, int& w0) {
+  const int n_full = tiles_per_img * p.B;
+  const int total_tiles = n_full + p.n_tail_tiles;
+  auto tile_coords = [&](int t, int& b_img, int& h0, int& w0) -> bool {  // returns true for a tail tile
     t = min(t, total_tiles - 1);  // tail of the last M group: reload the last tile, its epilogue is skipped
+    if (t >= n_full) {
+      const int u = t - n_full;
+      const int bg = u / p.tiles_x;
+      b_img = bg * p.tail_imgs;
+      h0 = p.tiles_y * p.th;
+      w0 = (u - bg * p.tiles_x) * p.tw;
+      return true;
+    }
     b_img = t / tiles_per_img;
     const int t_in = t - b_img * tiles_per_img;
     const int tyi = t_in / p.tiles_x;
     h0 = tyi * p.th;
     w0 = (t_in - tyi * p.tiles_x) * p.tw;
+    return false;
   };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
+    if (p.n_tail_tiles) tma_prefetch_desc(&p.tmOut);  // (normal kernel: tmOut holds the tail-tile input map)
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar + 8 * s, 1);
       mbar_init(empty_bar + 8 * s, 1);
@@ -83,14 +98,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
-      const uint32_t tx_bytes = static_cast<uint32_t>(p.mt) * static_cast<uint32_t>(p.tw * p.th) * kRowBytes + b_bytes;
+      const uint32_t full_tile_bytes = static_cast<uint32_t>(p.tw * p.th) * kRowBytes;
+      const uint32_t tail_tile_bytes = static_cast<uint32_t>(p.tw * p.tail_rows * p.tail_imgs) * kRowBytes;
       int stage = 0;
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
         const int mg = item / p.n_tiles;
         const int n0 = (item - mg * p.n_tiles) * p.block_n;
         int tb[4], th0[4], tw0[4];
-        for (int i = 0; i < p.mt; ++i) tile_coords(mg * p.mt + i, tb[i], th0[i], tw0[i]);
+        bool tail[4];
+        uint32_t tx_bytes = b_bytes;
+        for (int i = 0; i < p.mt; ++i) {
+          tail[i] = tile_coords(mg * p.mt + i, tb[i], th0[i], tw0[i]);
+          tx_bytes += tail[i] ? tail_tile_bytes : full_tile_bytes;
+        }
         int tap = 0, cb = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
@@ -99,7 +120,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
           const int ty = tap / p.kw;
           const int tx = tap - ty * p.kw;
           for (int i = 0; i < p.mt; ++i)
-            tma_load_4d(a_base + stage * a_stage_bytes + i * kABytes, &p.tmA, fb, p.cin_off + cb * BK,
+            tma_load_4d(a_base + stage * a_stage_bytes + i * kABytes, tail[i] ? &p.tmOut : &p.tmA, fb, p.cin_off + cb * BK,
                         tw0[i] * p.stride + tx - p.pad, th0[i] * p.stride + ty - p.pad, tb[i]);
           tma_load_2d(b_base + stage * b_bytes, &p.tmB, fb, tap * p.cin + cb * BK, n0);
           if (++cb == cblks) {
@@ -156,8 +177,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are the ones this warp may read
     const int chunk0 = ew >> 2;    // two warps share a quarter: even / odd 16-column chunks
     const int r = quarter * 32 + lane;
-    const int ly = r / p.tw;
-    const int lx = r - ly * p.tw;
     const int n_chunks = p.block_n >> 4;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -170,9 +189,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         const int tile = mg * p.mt + ti;
         if (tile >= total_tiles) break;
         int b_img, h0, w0;
-        tile_coords(tile, b_img, h0, w0);
+        const bool is_tail = tile_coords(tile, b_img, h0, w0);
+        int ly, lx;
+        bool row_ok;
+        if (is_tail) {  // rows = (image, row, col) of the left-over rows of tail_imgs images
+          const int per_img = p.tw * p.tail_rows;
+          const int il = r / per_img;
+          const int rr = r - il * per_img;
+          ly = rr / p.tw;
+          lx = rr - ly * p.tw;
+          b_img += il;
+          row_ok = (il < p.tail_imgs) && (b_img < p.B);
+        } else {
+          ly = r / p.tw;
+          lx = r - ly * p.tw;
+          row_ok = r < p.tw * p.th;
+        }
         const int oh = h0 + ly, ow = w0 + lx;
-        const bool row_ok = (r < p.tw * p.th) && (oh < p.Ho) && (ow < p.Wo);
+        row_ok = row_ok && (oh < p.Ho) && (ow < p.Wo);
         int n_shift = 0;  // channel shift when the n-tile addresses a sub-pixel of the 2x2 transpose conv
         int ph = oh, pw = ow;
         if (p.up) {
@@ -347,7 +381,7 @@ void conv_finalize(ConvLaunch& L) {
     return;
   }
   L.n_tiles = (L.n_total + L.block_n - 1) / L.block_n;
-  const int m_groups = (L.tiles_x * L.tiles_y * L.B + L.mt - 1) / L.mt;
+  const int m_groups = (L.tiles_x * L.tiles_y * L.B + L.n_tail_tiles + L.mt - 1) / L.mt;
   L.num_items = m_groups * L.n_tiles;
   L.acc_stages = (2 * L.mt * L.block_n <= 512) ? 2 : 1;
   int cols = 32;
@@ -371,6 +405,19 @@ int conv_make_tensor_maps(ConvLaunch& L, const void* in_base, int in_C, int in_H
     if (r != CUDA_SUCCESS) {
       snprintf(g_conv_err, sizeof(g_conv_err), "encode A map failed: %d (C=%d W=%d H=%d B=%d box %d,%d,%d s=%d)", (int)r,
                in_C, in_W, in_H, L.B, bk, L.tw, L.th, L.stride);
+      return 2;
+    }
+  }
+  if (!L.swap && L.n_tail_tiles > 0) {  // tail tiles: left-over rows of tail_imgs consecutive images
+    cuuint64_t dims[4] = {(cuuint64_t)in_C, (cuuint64_t)in_W, (cuuint64_t)in_H, (cuuint64_t)L.B};
+    cuuint64_t strides[3] = {(cuuint64_t)in_C * 2, (cuuint64_t)in_W * in_C * 2, (cuuint64_t)in_H * in_W * in_C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(L.tw * L.stride), (cuuint32_t)(L.tail_rows * L.stride), (cuuint32_t)L.tail_imgs};
+    cuuint32_t estr[4] = {1, (cuuint32_t)L.stride, (cuuint32_t)L.stride, 1};
+    CUresult r = enc(&L.tmOut, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in_base), dims, strides, box,
+                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      snprintf(g_conv_err, sizeof(g_conv_err), "encode tail map failed: %d (box %d,%d,%d,%d)", (int)r, bk, L.tw, L.tail_rows, L.tail_imgs);
       return 2;
     }
   }

@@ -39,6 +39,8 @@ struct ConvLaunch {
   int stages, tmem_cols;
   int mt;                        // M tiles (128-pixel accumulators) per work item sharing one weight stream
   int swap;                      // 1: operands swapped (conv_igemm_swap.cu): M = 128 cout rows, N = tw*th pixels
+  int tail_rows, tail_imgs, n_tail_tiles;  // normal kernel: left-over rows of tail_imgs images share one tile
+  int ks;                        // swapped kernel: k-blocks per pipeline stage (must divide taps*cin/BK)
   int ngroups, gw;               // swapped kernel: output-channel groups and channels per group (<= 128)
   int stg_bufs;                  // swapped kernel: epilogue staging tiles (2 = store of item i overlaps item i+1)
   int acc_stages, n_tiles, num_items;  // TMEM accumulator stages (1|2), N tiles, work items (persistent CTAs)

@@ -37,9 +37,10 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
   const int npix = p.tw * p.th;                                   // UMMA N (multiple of 16, <= 256)
   const uint32_t x_bytes = static_cast<uint32_t>(npix) * kRowBytes;  // pixel tile bytes
   const uint32_t x_slot = (x_bytes + 1023u) & ~1023u;
+  const int ks = p.ks;                                              // k-blocks per pipeline stage (one barrier round trip)
   const uint32_t w_base = smem_base;
-  const uint32_t x_base = w_base + p.stages * kWBytes;
-  const uint32_t stage_base = x_base + p.stages * x_slot;                  // epilogue tile [npix][n_total] bf16
+  const uint32_t x_base = w_base + p.stages * ks * kWBytes;
+  const uint32_t stage_base = x_base + p.stages * ks * x_slot;             // epilogue tile [npix][n_total] bf16
   const int gw = p.gw;                                                     // channels per group (<= 128)
   const uint32_t esz = p.out_fp32 ? 4u : 2u;
   const uint32_t stage_bytes = static_cast<uint32_t>(npix * gw) * esz;
@@ -103,18 +104,20 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
         const int tyi = t_in / p.tiles_x;
         const int h0 = tyi * p.th, w0 = (t_in - tyi * p.tiles_x) * p.tw;
         int tap = 0, cb = 0;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = 0; kb < num_kb; kb += ks) {
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
           const uint32_t fb = full_bar + 8 * stage;
-          mbar_arrive_expect_tx(fb, tx_bytes);
-          const int ty = tap / p.kw;
-          const int tx = tap - ty * p.kw;
-          tma_load_4d(x_base + stage * x_slot, &p.tmA, fb, p.cin_off + cb * BK, w0 * p.stride + tx - p.pad,
-                      h0 * p.stride + ty - p.pad, b_img);
-          tma_load_2d(w_base + stage * kWBytes, &p.tmB, fb, tap * p.cin + cb * BK, n_base);
-          if (++cb == cblks) {
-            cb = 0;
-            ++tap;
+          mbar_arrive_expect_tx(fb, tx_bytes * ks);
+          for (int q = 0; q < ks; ++q) {
+            const int ty = tap / p.kw;
+            const int tx = tap - ty * p.kw;
+            tma_load_4d(x_base + (stage * ks + q) * x_slot, &p.tmA, fb, p.cin_off + cb * BK, w0 * p.stride + tx - p.pad,
+                        h0 * p.stride + ty - p.pad, b_img);
+            tma_load_2d(w_base + (stage * ks + q) * kWBytes, &p.tmB, fb, tap * p.cin + cb * BK, n_base);
+            if (++cb == cblks) {
+              cb = 0;
+              ++tap;
+            }
           }
           if (++stage == p.stages) {
             stage = 0;
@@ -135,13 +138,16 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
         mbar_wait(tmem_empty_bar + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d = tmem_acc + acc * acc_cols;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = 0; kb < num_kb; kb += ks) {
           mbar_wait(full_bar + 8 * stage, phase);
           tc_fence_after();
-          const uint64_t w_desc = umma_smem_desc(w_base + stage * kWBytes, kRowBytes);  // M side: weights
-          const uint64_t x_desc = umma_smem_desc(x_base + stage * x_slot, kRowBytes);   // N side: pixels
+          for (int q = 0; q < ks; ++q) {
+            const uint64_t w_desc = umma_smem_desc(w_base + (stage * ks + q) * kWBytes, kRowBytes);  // M side: weights
+            const uint64_t x_desc = umma_smem_desc(x_base + (stage * ks + q) * x_slot, kRowBytes);   // N side: pixels
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) umma_bf16(d, w_desc + 2 * k, x_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16(d, w_desc + 2 * k, x_desc + 2 * k, idesc, (kb | q | k) != 0 ? 1u : 0u);
+          }
           umma_commit(empty_bar + 8 * stage);
           if (++stage == p.stages) {
             stage = 0;
@@ -264,7 +270,7 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
 size_t conv_swap_smem_bytes(const ConvLaunch& L, int bk) {
   const size_t x_slot = (static_cast<size_t>(L.tw * L.th) * bk * 2 + 1023) & ~static_cast<size_t>(1023);
   const size_t staging = (static_cast<size_t>(L.tw * L.th) * L.gw * (L.out_fp32 ? 4 : 2) + 1023) & ~static_cast<size_t>(1023);
-  return 1024 + static_cast<size_t>(L.stages) * (128 * bk * 2 + x_slot) + L.stg_bufs * staging + 16 * L.stages + 128;
+  return 1024 + static_cast<size_t>(L.stages) * L.ks * (128 * bk * 2 + x_slot) + L.stg_bufs * staging + 16 * L.stages + 128;
 }
 
 template <int BK>

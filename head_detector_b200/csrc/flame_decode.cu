@@ -120,9 +120,6 @@ __global__ void __launch_bounds__(kTileV* HG) flame_decode_kernel(const FlameArg
   constexpr int kVTiles = kVPad / kTileV;
   const int n_items = kVTiles * ((n_heads + kHeads - 1) / kHeads);
   const int tid = threadIdx.x;
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-  const int head0 = (item / kVTiles) * kHeads;
-  const int v0 = (item % kVTiles) * kTileV;
   const int vl = tid % kTileV;
   const int grp = tid / kTileV;
   const int lb = a.ns + a.ne;          // live blendshape coefficients
@@ -135,8 +132,13 @@ __global__ void __launch_bounds__(kTileV* HG) flame_decode_kernel(const FlameArg
   double* beta_s = sd_s + 2 * kLc * kTileV * 3;                         // [lt_pad][kHeads]
   double* tj_s = beta_s + static_cast<size_t>(lt_pad) * kHeads;         // [kHeads][3]
   double* r2_s = tj_s + kHeads * 3;                                     // [kHeads][9]
-  float* R_s = reinterpret_cast<float*>(r2_s + kHeads * 9);             // [kHeads][9]
+  double* js2_s = r2_s + kHeads * 9;                                    // [3][400] jaw-joint regressor x shape basis
+  float* R_s = reinterpret_cast<float*>(js2_s + 3 * kL);                // [kHeads][9]
   float* st_s = R_s + kHeads * 9;                                       // [kHeads][8]: scale,tx,ty,tz,padx,pady,iscale
+  for (int i = tid; i < 3 * kL; i += blockDim.x) js2_s[i] = a.c.js2[i];  // once per CTA (coalesced), reused by every item
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+  const int head0 = (item / kVTiles) * kHeads;
+  const int v0 = (item % kVTiles) * kTileV;
 
   // ---- prologue: betas (fp64), per-head rotations
   for (int idx = tid; idx < lb * kHeads; idx += blockDim.x) {
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(kTileV* HG) flame_decode_kernel(const FlameArg
     if (live) {
       for (int i = part; i < lb; i += 4) {
         const int l = i < a.ns ? i : 300 + (i - a.ns);
-        acc = fma(a.c.js2[k * kL + l], beta_s[i * kHeads + h], acc);
+        acc = fma(js2_s[k * kL + l], beta_s[i * kHeads + h], acc);
       }
     }
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
@@ -303,7 +305,7 @@ struct FlameModel {
 };
 
 static size_t flame_smem_bytes(int heads, int lt_pad) {
-  return sizeof(double) * (2 * kLc * kTileV * 3 + static_cast<size_t>(lt_pad) * heads + heads * 3 + heads * 9) +
+  return sizeof(double) * (2 * kLc * kTileV * 3 + static_cast<size_t>(lt_pad) * heads + heads * 3 + heads * 9 + 3 * kL) +
          sizeof(float) * (heads * 9 + heads * 8);
 }
 

@@ -137,6 +137,26 @@ class Engine:
             out["verts"].data_ptr(), out["verts"].shape[0], total.data_ptr(), _lib.stream_ptr()), "run_host")
         return int(total[0])
 
+    def submit_device(self, conf=0.5, iou=0.5, top_k=1000) -> int:
+        """Graph replay over the staging input + snapshot of the results into a slot (returned)."""
+        slot = C.c_int32(-1)
+        _lib.check(_lib.lib().vgh_detector_submit_device(self._h, conf, iou, top_k, _lib.stream_ptr(), C.byref(slot)), "submit_device")
+        return slot.value
+
+    def slot_views(self, slot: int, n_heads: int):
+        """Zero-copy views of a snapshot slot: dict(keep_cnt, boxes, scores, params, verts)."""
+        def v(which, shape, ts="<f4"):
+            return torch.as_tensor(_DevView(_lib.lib().vgh_detector_slot_output(self._h, slot, which), shape, ts), device="cuda")
+        return {"keep_cnt": v(_lib.OUT_KEEP_CNT, (self.B,), "<i4"), "boxes": v(_lib.OUT_KEEP_BOXES, (self.B * self.keep_k, 4)),
+                "scores": v(_lib.OUT_KEEP_SCORES, (self.B * self.keep_k,)), "params": v(_lib.OUT_HEAD_PARAMS, (max(n_heads, 1), _lib.NUM_PARAMS))[:n_heads],
+                "verts": v(_lib.OUT_HEAD_VERTS, (max(n_heads, 1), _lib.NUM_VERTS, 3))[:n_heads]}
+
+    def slot_total(self, slot: int) -> torch.Tensor:
+        return torch.as_tensor(_DevView(_lib.lib().vgh_detector_slot_output(self._h, slot, _lib.OUT_HEAD_OFFSETS), (1,), "<i4"), device="cuda")
+
+    def release_slot(self, slot: int):
+        _lib.check(_lib.lib().vgh_detector_release_slot(self._h, slot, _lib.stream_ptr()), "release_slot")
+
     def submit_host(self, images_host: torch.Tensor, conf=0.5, iou=0.5, top_k=1000):
         """Pipelined end-to-end: enqueue upload + compute + result staging of one batch (max 2 in flight)."""
         _lib.check(_lib.lib().vgh_detector_submit_host(self._h, images_host.data_ptr(), conf, iou, top_k), "submit_host")

@@ -14,37 +14,41 @@ def shard_range(total: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def gather_predictions(local: Dict[str, torch.Tensor], dst: int = 0, group=None) -> Optional[Dict[str, torch.Tensor]]:
-    """Ragged gather: `local` holds keep_cnt [b] int32 and per-head tensors (first dim = number of
-    local heads, image-major).  Step 1 all-gathers the per-rank head totals and image counts,
-    step 2 gathers each per-head tensor padded to the largest rank.  Returns the concatenated
-    dict on `dst`, None elsewhere."""
+FIXED_KEYS = ("keep_cnt", "boxes", "scores")  # per-image, fixed-capacity tensors: gathered as they are
+
+
+def gather_predictions(local: Dict[str, torch.Tensor], dst: int = 0, group=None, n_heads: Optional[int] = None) -> Optional[Dict[str, torch.Tensor]]:
+    """Ragged gather of one step's predictions to rank `dst`.
+
+    `local`: keep_cnt [b] int32 plus tensors keyed by name.  Keys in FIXED_KEYS have the same shape on
+    every rank (per-image capacity buffers) and are gathered directly; all other tensors have the
+    number of local heads as first dim (image-major) and are padded to the largest rank.  One tiny
+    all-gather of the head totals, then one `dist.gather` per tensor.  Returns the concatenated dict
+    on `dst`, None elsewhere."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     cnt = local["keep_cnt"]
     dev = cnt.device
-    n_local = torch.tensor([int(cnt.sum()), cnt.numel()], device=dev, dtype=torch.int64)
-    sizes = [torch.zeros_like(n_local) for _ in range(world)]
-    dist.all_gather(sizes, n_local, group=group)
+    if n_heads is None:
+        n_heads = int(cnt.sum())
+    mine = torch.tensor([n_heads], device=dev, dtype=torch.int64)
+    sizes = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(sizes, mine, group=group)
     heads = [int(s[0]) for s in sizes]
-    imgs = [int(s[1]) for s in sizes]
-    max_heads, max_imgs = max(heads + [1]), max(imgs)
+    max_heads = max(heads + [1])
     out = {} if rank == dst else None
-
-    def gather_padded(t, n_rows, max_rows, counts):
-        pad = torch.zeros((max_rows,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
-        pad[:n_rows] = t[:n_rows]
+    for key, t in local.items():
+        if key in FIXED_KEYS:
+            src = t.contiguous()
+            bufs = [torch.empty_like(src) for _ in range(world)] if rank == dst else None
+            dist.gather(src, bufs, dst=dst, group=group)
+            if rank == dst:
+                out[key] = torch.cat(bufs)
+            continue
+        pad = torch.zeros((max_heads,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+        pad[:n_heads] = t[:n_heads]
         bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
         dist.gather(pad, bufs, dst=dst, group=group)
-        return torch.cat([b[:c] for b, c in zip(bufs, counts)]) if rank == dst else None
-
-    g = gather_padded(cnt, cnt.numel(), max_imgs, imgs)
-    if rank == dst:
-        out["keep_cnt"] = g
-    for key, t in local.items():
-        if key == "keep_cnt":
-            continue
-        g = gather_padded(t, heads[rank], max_heads, heads)
         if rank == dst:
-            out[key] = g
+            out[key] = torch.cat([b[:c] for b, c in zip(bufs, heads)])
     return out

@@ -153,6 +153,14 @@ int vgh_detector_run_host(vgh_detector* d, const uint8_t* images_host, const flo
 int vgh_detector_submit_host(vgh_detector* d, const uint8_t* images_host, float conf_thr, float iou_thr, int top_k);
 int vgh_detector_collect_host(vgh_detector* d, int32_t* keep_cnt_host, float* keep_boxes_host, float* keep_scores_host,
                               float* params_host, float* verts_host, int max_heads, int32_t* total_heads);
+/* Device-resident pipeline step for multi-GPU runs: graph replay over the staging input + snapshot of
+ * the results into one of two slots (returned in *slot_out), so that the gather of this step can run
+ * on another stream while the next step computes.  vgh_detector_slot_output(slot, VGH_OUT_*) gives the
+ * snapshot pointers (KEEP_CNT, KEEP_BOXES, KEEP_SCORES, HEAD_PARAMS, HEAD_VERTS, HEAD_OFFSETS -> total);
+ * vgh_detector_release_slot(slot, consumer_stream) hands the slot back once the consumer's work is queued. */
+int vgh_detector_submit_device(vgh_detector* d, float conf_thr, float iou_thr, int top_k, void* stream, int32_t* slot_out);
+int vgh_detector_release_slot(vgh_detector* d, int slot, void* consumer_stream);
+void* vgh_detector_slot_output(vgh_detector* d, int slot, int which);
 /* Same device work (graph replay) with inputs already resident in the internal staging buffer and
  * results left on the device - the kernel-only timing path. */
 int vgh_detector_run_device(vgh_detector* d, float conf_thr, float iou_thr, int top_k, void* stream);

@@ -18,10 +18,10 @@ def _free_port():
 
 
 def _local(rank):
-    cnt = torch.tensor([2, 0, 1], dtype=torch.int32) if rank == 0 else torch.tensor([0, 4], dtype=torch.int32)
+    cnt = torch.tensor([2, 0, 1], dtype=torch.int32) if rank == 0 else torch.tensor([0, 4, 0], dtype=torch.int32)
     n = int(cnt.sum())
     g = torch.Generator().manual_seed(rank)
-    return {"keep_cnt": cnt, "scores": torch.rand(n, generator=g), "params": torch.rand(n, 413, generator=g),
+    return {"keep_cnt": cnt, "rot": torch.rand(n, 9, generator=g), "params": torch.rand(n, 413, generator=g),
             "verts": torch.rand(n, 7, 3, generator=g)}
 
 
@@ -57,6 +57,6 @@ def test_ragged_gather_two_ranks():
         p.join(60)
         assert p.exitcode == 0
     a, b = _local(0), _local(1)
-    assert out["keep_cnt"].tolist() == [2, 0, 1, 0, 4]
-    for k in ("scores", "params", "verts"):
+    assert out["keep_cnt"].tolist() == [2, 0, 1, 0, 4, 0]
+    for k in ("rot", "params", "verts"):
         assert torch.equal(out[k], torch.cat([a[k], b[k]]))

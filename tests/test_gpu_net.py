@@ -195,3 +195,24 @@ def test_highres_1280_many_heads():
     assert torch.isfinite(rows).all() and torch.isfinite(eng.boxes).all()
     ref = flame_oracle.detector_vertices(rows, flame_oracle.load_flame_constants())
     assert (eng.head_verts(n).cpu() - ref).abs().max() < 2e-4   # coordinates up to 1280: 1 ulp = 1.2e-4
+
+
+def test_key_buffers_640_batch3_vs_cpu_interpretation():
+    """Reference resolution, odd batch: exercises the 40x40 / 20x20 tilings (incl. tiles that pack the
+    left-over rows of several images) against the CPU interpretation of the same plan."""
+    from head_detector_b200 import synth
+    from head_detector_b200.engine import Engine
+
+    B, S = 3, 640
+    eng = Engine(no.synthetic_weights(5), B, S)
+    img = synth.synthetic_images(B, S, seed=11)
+    eng.forward(img.cuda())
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = pe.run_plan(eng.packed, img, emulate_bf16=True)
+    for name in ("c3", "c4", "c5", "p4", "p5", "head2.flame_raw", "head3.reg_raw", "head1.reg_raw"):
+        got, want = eng.read_buffer(name), ref[eng.plan.buf_names[name]]
+        scale = want.abs().max().item() + 1e-6
+        err = (got - want).abs()
+        assert err.max().item() <= 2 ** -5 * scale + 1e-4, (name, err.max().item(), scale)
+        assert err.mean().item() <= 4e-3 * scale, (name, err.mean().item(), scale)

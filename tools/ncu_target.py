@@ -17,7 +17,7 @@ img = synth.synthetic_images(B, 640, 0).cuda()
 boxes, scores = synth.engineered_heads(B, eng.A, 640, 8, seed=7)
 eng.set_override(boxes.cuda(), scores.cuda())
 if tune:
-    eng.autotune(3)
+    eng.autotune(5)
 for _ in range(2):
     eng.forward(img)
     eng.postprocess(0.5, 0.5, 1000)

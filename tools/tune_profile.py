@@ -13,7 +13,7 @@ eng.input.copy_(synth.synthetic_images(B, 640, 0).cuda())
 boxes, scores = synth.engineered_heads(B, eng.A, 640, 8, seed=7)
 eng.set_override(boxes.cuda(), scores.cuda())
 if tune:
-    eng.autotune(3)
+    eng.autotune(5)
 eng.profile(iters=2)
 rows = eng.profile(iters=10)
 tot = sum(t for _, t, _ in rows); conv_ms = sum(t for _, t, f in rows if f); conv_fl = sum(f for _, t, f in rows if f)
