@@ -216,3 +216,36 @@ def test_key_buffers_640_batch3_vs_cpu_interpretation():
         err = (got - want).abs()
         assert err.max().item() <= 2 ** -5 * scale + 1e-4, (name, err.max().item(), scale)
         assert err.mean().item() <= 4e-3 * scale, (name, err.mean().item(), scale)
+
+
+def test_two_detector_handles_run_concurrently():
+    """Two handles on two streams (two batches in flight, as bench.py runs them) give exactly the
+    results each gives alone."""
+    from head_detector_b200 import synth
+    from head_detector_b200.engine import Engine
+
+    B, S = 2, 640
+    w = no.synthetic_weights(0)
+    engs = [Engine(w, B, S) for _ in range(2)]
+    boxes, scores = synth.engineered_heads(B, engs[0].A, S, heads=6, per_cluster=10, seed=12)
+    imgs = [synth.synthetic_images(B, S, seed=70 + i).cuda() for i in range(2)]
+    alone = []
+    for e, im in zip(engs, imgs):
+        e.set_override(boxes.cuda(), scores.cuda())
+        e.input.copy_(im)
+        e.run_device()
+        torch.cuda.synchronize()
+        n = int(e.head_offsets[-1])
+        alone.append((n, e.keep_idx.clone(), e.head_params(n).clone(), e.head_verts(n).clone(), e.boxes.clone()))
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for _ in range(3):
+        for e, im, st in zip(engs, imgs, streams):
+            with torch.cuda.stream(st):
+                e.input.copy_(im, non_blocking=True)
+                e.run_device()
+    torch.cuda.synchronize()
+    for e, ref in zip(engs, alone):
+        n = int(e.head_offsets[-1])
+        assert n == ref[0] > 0
+        assert torch.equal(e.keep_idx, ref[1]) and torch.equal(e.head_params(n), ref[2])
+        assert torch.equal(e.head_verts(n), ref[3]) and torch.equal(e.boxes, ref[4])
