@@ -209,10 +209,6 @@ def run_ours(args, rank, world, local_rank):
     stream = torch.cuda.current_stream()
     lanes = [torch.cuda.Stream() for _ in engs]
 
-    def local_predictions(n):
-        return {"keep_cnt": eng.keep_cnt, "boxes": eng.keep_boxes.reshape(-1, 4), "scores": eng.keep_scores.reshape(-1),
-                "params": eng.head_params(n), "verts": eng.head_verts(n)}
-
     # N > 1: the one exchange of the path - a ragged gather of predictions to rank 0 - runs on a side
     # stream from a snapshot slot while the following steps compute (it is still part of every step)
     side = torch.cuda.Stream() if world > 1 else None
@@ -285,41 +281,43 @@ def run_ours(args, rank, world, local_rank):
     heads_total = int(eng.head_offsets[-1])
 
     # end to end through the host-buffer C-ABI: every step uploads its images from pinned host memory
-    # and downloads counts / boxes / scores / params / vertices.  N=1: submit/collect pipeline over the
-    # two engines (copies of the neighbouring steps overlap compute); N>1: synchronous call + NCCL gather.
-    def host_step(i):
-        eng.run_host(host_imgs[i % n_rot], out, CONF, IOU, TOPK)
+    # and downloads counts / boxes / scores / params / vertices: submit/collect pipeline over the two
+    # engines (copies of the neighbouring steps overlap compute); N > 1 adds the NCCL gather per step.
+    collected = {id(e): 0 for e in engs}
+
+    def collect_and_gather(e):
+        """Download the oldest batch of engine e; N > 1: then gather it to rank 0 from the snapshot slot
+        (device memory) on the side stream - the slot is handed back once the gather is queued."""
+        n = e.collect_host(out)
+        slot = collected[id(e)] & 1
+        collected[id(e)] += 1
         if world > 1:
-            parallel.gather_predictions(local_predictions(int(out["total"][0])))
+            with torch.cuda.stream(side):
+                parallel.gather_predictions(e.slot_views(slot, n), n_heads=n)
+                e.release_slot(slot)
 
     def pipelined_host(steps):
-        """K steps, up to 2 per engine in flight; returns after every result is on the host."""
+        """K steps, up to 3 in flight over the two engines; returns after every result is on the host
+        (and, for N > 1, gathered on rank 0)."""
         inflight = []
         for i in range(steps):
             e = engs[i % len(engs)]
             if len(inflight) >= 2 * len(engs) - 1:
-                inflight.pop(0).collect_host(out)
+                collect_and_gather(inflight.pop(0))
             e.submit_host(host_imgs[i % n_rot], CONF, IOU, TOPK)
             inflight.append(e)
         while inflight:
-            inflight.pop(0).collect_host(out)
+            collect_and_gather(inflight.pop(0))
+        if side is not None:
+            stream.wait_stream(side)
 
-    if world == 1:
-        pipelined_host(4)
-        sync_all()
-        t0 = time.perf_counter()
-        pipelined_host(args.steps)
-        sync_all()
-        e2e_s = time.perf_counter() - t0
-    else:
-        for i in range(3):
-            host_step(i)
-        sync_all()
-        t0 = time.perf_counter()
-        for i in range(args.steps):
-            host_step(i)
-        sync_all()
-        e2e_s = time.perf_counter() - t0
+    pipelined_host(4)
+    sync_all()
+    t0 = time.perf_counter()
+    pipelined_host(args.steps)
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
         t = torch.tensor([e2e_s], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t[0])
@@ -365,7 +363,7 @@ def run_ours(args, rank, world, local_rank):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": _config(world),
             "clocks": clocks,
             "e2e": {"value": imgs / e2e_s, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "mode": "vgh_detector_submit_host/collect_host over 2 detector handles (3 batches in flight)" if world == 1 else "vgh_detector_run_host + NCCL gather"},
+                    "mode": "vgh_detector_submit_host/collect_host over 2 detector handles (3 batches in flight)" + (" + NCCL gather of every step" if world > 1 else "")},
             "gpu_launches": eng.launch_count * args.steps,
             "roofline": roof, "cpu_baseline": cpu_base,
             "heads_per_step_per_gpu": heads_total,
