@@ -12,14 +12,14 @@ from head_detector_b200.engine import Engine  # noqa: E402
 
 B, S, steps = 32, 640, int(sys.argv[1]) if len(sys.argv) > 1 else 40
 w = arch.synthetic_weights(0)
-engs = [Engine(w, B, S) for _ in range(2)]
+engs = [Engine(w, B, S) for _ in range(3)]
 boxes, scores = synth.engineered_heads(B, engs[0].A, S, 8, seed=7)
 bd, sd = boxes.cuda(), scores.cuda()
 imgs = [synth.synthetic_images(B, S, i).cuda() for i in range(4)]
 for e in engs:
     e.set_override(bd, sd)
     e.autotune(5)
-streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+streams = [torch.cuda.Stream() for _ in engs]
 
 
 def run(n_eng):
@@ -44,6 +44,6 @@ def run(n_eng):
     return ms, B / ms * 1e3
 
 
-for n in (1, 2, 1, 2):
+for n in (1, 2, 3, 1, 2, 3):
     ms, ips = run(n)
     print(f"{n} batch(es) in flight: {ms:.3f} ms/step, {ips:.0f} img/s", flush=True)
