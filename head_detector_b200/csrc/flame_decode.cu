@@ -12,8 +12,9 @@
 //
 // Work decomposition: item = 128 vertices x (8*HG heads), persistent CTAs walk the items.  Each thread owns one vertex (3 coords) for
 // 8 heads = 24 fp64 accumulators.  The shape basis slab of the CTA's 128 vertices streams through a
-// double-buffered cp.async pipeline (8 coefficients per stage) and is shared by the HG head groups;
-// betas live in shared memory as fp64 and are read as broadcast 128-bit loads.
+// 4-stage cp.async pipeline (8 coefficients per stage) as fp32 - the precision the reference holds it
+// in - and is widened exactly to fp64 in registers; it is shared by the HG head groups.  Betas live in
+// shared memory as fp64 and are read as broadcast 128-bit loads.
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -32,12 +33,14 @@ constexpr int kL = 400;
 constexpr int kTileV = 128;
 constexpr int kHPT = 8;   // heads per thread
 constexpr int kLc = 8;    // coefficients per pipeline stage
+constexpr int kNS = 4;    // pipeline stages of the basis stream
 constexpr int kNPose = 9; // live pose-corrective rows (jaw joint only)
 constexpr int kParams = 413;
 
 struct FlameDev {
-  double* sdt;   // [400][kVPad][3]  shape basis, coefficient-major
-  double* pd;    // [9][kVPad][3]    posedirs rows 9..17 (jaw)
+  float* sdt;    // [400][kVPad][3]  shape basis, coefficient-major (fp32 as the reference holds it; widened
+                 //                  exactly to fp64 in registers - half the L2 / shared-memory traffic of an fp64 copy)
+  float* pd;     // [9][kVPad][3]    posedirs rows 9..17 (jaw)
   double* vt;    // [kVPad][3]       template
   double* wI;    // [kVPad]          W0+W1+W3+W4
   double* w2;    // [kVPad]          W2 (jaw)
@@ -112,7 +115,7 @@ __device__ void rodrigues_f32(const float* r, float* R) {
 }
 
 template <int HG>
-__global__ void __launch_bounds__(kTileV* HG) flame_decode_kernel(const FlameArgs a) {
+__global__ void __launch_bounds__(kTileV* HG, HG == 1 ? 4 : 3) flame_decode_kernel(const FlameArgs a) {
   constexpr int kHeads = kHPT * HG;
   const int n_heads = a.n_dev ? min(*a.n_dev, a.n) : a.n;
   // work items = (vertex tile, head group); CTAs walk them with a grid stride so that the device-side
@@ -128,8 +131,8 @@ __global__ void __launch_bounds__(kTileV* HG) flame_decode_kernel(const FlameArg
   const int lt_pad = n_chunks * kLc;
 
   extern __shared__ __align__(16) uint8_t smem[];
-  double* sd_s = reinterpret_cast<double*>(smem);                       // [2][kLc][128][3]
-  double* beta_s = sd_s + 2 * kLc * kTileV * 3;                         // [lt_pad][kHeads]
+  float* sd_s = reinterpret_cast<float*>(smem);                         // [kNS][kLc][128][3] fp32
+  double* beta_s = reinterpret_cast<double*>(sd_s + kNS * kLc * kTileV * 3);  // [lt_pad][kHeads]
   double* tj_s = beta_s + static_cast<size_t>(lt_pad) * kHeads;         // [kHeads][3]
   double* r2_s = tj_s + kHeads * 3;                                     // [kHeads][9]
   double* js2_s = r2_s + kHeads * 9;                                    // [3][400] jaw-joint regressor x shape basis
@@ -209,40 +212,40 @@ __global__ void __launch_bounds__(kTileV* HG) flame_decode_kernel(const FlameArg
     for (int h = 0; h < kHPT; ++h) { acc[h][0] = t0; acc[h][1] = t1; acc[h][2] = t2; }
   }
   const uint32_t sd_smem = static_cast<uint32_t>(__cvta_generic_to_shared(sd_s));
-  constexpr int kRowBytes = kTileV * 3 * 8;            // 3072 B per coefficient row
-  constexpr int kStageBytes = kLc * kRowBytes;         // 24576 B
-  constexpr int kVecPerStage = kStageBytes / 16;       // 1536
-  auto issue = [&](int chunk, int buf) {
-    for (int q = tid; q < kVecPerStage; q += blockDim.x) {
-      const int row = q / (kRowBytes / 16);
-      const int off = q - row * (kRowBytes / 16);
-      int i = chunk * kLc + row;
-      const double* src;
-      if (i < lb) {
-        const int l = i < a.ns ? i : 300 + (i - a.ns);
-        src = a.c.sdt + (static_cast<size_t>(l) * kVPad + v0) * 3;
-      } else {
-        const int m = min(i - lb, kNPose - 1);  // rows past the end multiply a zero beta
-        src = a.c.pd + (static_cast<size_t>(m) * kVPad + v0) * 3;
+  constexpr int kRowBytes = kTileV * 3 * 4;            // 1536 B per coefficient row (fp32)
+  constexpr int kStageBytes = kLc * kRowBytes;         // 12288 B
+  constexpr int kVecPerStage = kStageBytes / 16;       // 768
+  auto issue = [&](int chunk) {
+    if (chunk < n_chunks) {
+      const int buf = chunk % kNS;
+      for (int q = tid; q < kVecPerStage; q += blockDim.x) {
+        const int row = q / (kRowBytes / 16);
+        const int off = q - row * (kRowBytes / 16);
+        const int i = chunk * kLc + row;
+        const float* src;
+        if (i < lb) {
+          const int l = i < a.ns ? i : 300 + (i - a.ns);
+          src = a.c.sdt + (static_cast<size_t>(l) * kVPad + v0) * 3;
+        } else {
+          const int m = min(i - lb, kNPose - 1);  // rows past the end multiply a zero beta
+          src = a.c.pd + (static_cast<size_t>(m) * kVPad + v0) * 3;
+        }
+        cp_async16(sd_smem + buf * kStageBytes + row * kRowBytes + off * 16, reinterpret_cast<const uint8_t*>(src) + off * 16);
       }
-      cp_async16(sd_smem + buf * kStageBytes + row * kRowBytes + off * 16, reinterpret_cast<const uint8_t*>(src) + off * 16);
     }
-    cp_async_commit();
+    cp_async_commit();  // (possibly empty) one group per chunk keeps the wait arithmetic uniform
   };
-  issue(0, 0);
+  for (int c = 0; c < kNS - 1; ++c) issue(c);
   for (int c = 0; c < n_chunks; ++c) {
-    if (c + 1 < n_chunks) {
-      issue(c + 1, (c + 1) & 1);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();
-    const double* sd = sd_s + (c & 1) * (kLc * kTileV * 3) + vl * 3;
+    cp_async_wait<kNS - 2>();  // chunk c has landed (groups complete in order)
+    __syncthreads();           // ... for every thread; and the buffer of chunk c-1 is free again
+    issue(c + kNS - 1);
+    const float* sd = sd_s + (c % kNS) * (kLc * kTileV * 3) + vl * 3;
     const double* bt = beta_s + static_cast<size_t>(c) * kLc * kHeads + grp * kHPT;
 #pragma unroll
     for (int r = 0; r < kLc; ++r) {
-      const double s0 = sd[r * kTileV * 3], s1 = sd[r * kTileV * 3 + 1], s2 = sd[r * kTileV * 3 + 2];
+      const double s0 = static_cast<double>(sd[r * kTileV * 3]), s1 = static_cast<double>(sd[r * kTileV * 3 + 1]),
+                   s2 = static_cast<double>(sd[r * kTileV * 3 + 2]);
       const double2* b2 = reinterpret_cast<const double2*>(bt + r * kHeads);
 #pragma unroll
       for (int hh = 0; hh < kHPT / 2; ++hh) {
@@ -255,8 +258,9 @@ __global__ void __launch_bounds__(kTileV* HG) flame_decode_kernel(const FlameArg
         acc[2 * hh + 1][2] = fma(s2, b.y, acc[2 * hh + 1][2]);
       }
     }
-    __syncthreads();
   }
+  cp_async_wait<0>();
+  __syncthreads();
 
   // ---- epilogue: skinning + rigid transform, per head
   const int v = v0 + vl;
@@ -305,20 +309,23 @@ struct FlameModel {
 };
 
 static size_t flame_smem_bytes(int heads, int lt_pad) {
-  return sizeof(double) * (2 * kLc * kTileV * 3 + static_cast<size_t>(lt_pad) * heads + heads * 3 + heads * 9 + 3 * kL) +
+  return sizeof(float) * (kNS * kLc * kTileV * 3) +
+         sizeof(double) * (static_cast<size_t>(lt_pad) * heads + heads * 3 + heads * 9 + 3 * kL) +
          sizeof(float) * (heads * 9 + heads * 8);
 }
 
 int flame_model_create(const float* v_template, const float* shapedirs, const float* posedirs, const float* j_regressor,
                        const float* lbs_weights, FlameModel** out, char* err, size_t errlen) {
-  // host re-layout in fp64 (exact widening of the fp32 constants the reference holds)
+  // host re-layout: the two big tables stay fp32 (coefficient-major); the small per-vertex / per-joint
+  // tables are widened to fp64 once (exact)
   const size_t n_sdt = static_cast<size_t>(kL) * kVPad * 3, n_pd = static_cast<size_t>(kNPose) * kVPad * 3;
   const size_t n_vt = static_cast<size_t>(kVPad) * 3, n_w = kVPad, n_js = 3 * kL;
-  const size_t total = n_sdt + n_pd + n_vt + 2 * n_w + n_js;
-  std::vector<double> host(total, 0.0);
-  double* sdt = host.data();
-  double* pd = sdt + n_sdt;
-  double* vt = pd + n_pd;
+  const size_t total_d = n_vt + 2 * n_w + n_js;
+  std::vector<float> hostf(n_sdt + n_pd, 0.f);
+  std::vector<double> host(total_d, 0.0);
+  float* sdt = hostf.data();
+  float* pd = sdt + n_sdt;
+  double* vt = host.data();
   double* wI = vt + n_vt;
   double* w2 = wI + n_w;
   double* js2 = w2 + n_w;
@@ -349,8 +356,10 @@ int flame_model_create(const float* v_template, const float* shapedirs, const fl
       js2[k * kL + l] = s;
     }
   }
-  cudaError_t e = cudaMalloc(&m->blob, total * sizeof(double));
-  if (e == cudaSuccess) e = cudaMemcpy(m->blob, host.data(), total * sizeof(double), cudaMemcpyHostToDevice);
+  const size_t bytes_d = total_d * sizeof(double), bytes_f = hostf.size() * sizeof(float);
+  cudaError_t e = cudaMalloc(&m->blob, bytes_d + bytes_f);
+  if (e == cudaSuccess) e = cudaMemcpy(m->blob, host.data(), bytes_d, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(static_cast<uint8_t*>(m->blob) + bytes_d, hostf.data(), bytes_f, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
     snprintf(err, errlen, "flame_model_create: %s", cudaGetErrorString(e));
     if (m->blob) cudaFree(m->blob);
@@ -358,12 +367,13 @@ int flame_model_create(const float* v_template, const float* shapedirs, const fl
     return 1;
   }
   double* d = static_cast<double*>(m->blob);
-  m->dev.sdt = d; d += n_sdt;
-  m->dev.pd = d; d += n_pd;
   m->dev.vt = d; d += n_vt;
   m->dev.wI = d; d += n_w;
   m->dev.w2 = d; d += n_w;
-  m->dev.js2 = d;
+  m->dev.js2 = d; d += n_js;
+  float* f = reinterpret_cast<float*>(d);  // bytes_d is a multiple of 16: the fp32 tables stay 16-byte aligned
+  m->dev.sdt = f;
+  m->dev.pd = f + n_sdt;
   *out = m;
   return 0;
 }
