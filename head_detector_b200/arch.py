@@ -5,7 +5,8 @@ Architecture source: the reference's arch spec
 `yolo_head_training/yolo_head/yolo_head_dfl_head.py:23-135` (per-level head) and the YoloNAS
 building blocks of super_gradients (stem / stage / CSP / SPP / up- / down-stage; SURVEY.md
 Appendix A.1).  Everything is in DEPLOY form: each QARepVGG block or Conv-BN-ReLU is one conv +
-bias + ReLU (Appendix A.2); `fold_*` helpers below produce that form from as-trained tensors.
+bias + ReLU (Appendix A.2); `fold_qarepvgg` / `fold_conv_bn` / `deploy_from_unfused` below produce that form
+from as-trained tensors.
 
 What this module adds on top of the spec is the B200 data layout:
   * activations are NHWC bf16 buffers; every conv writes straight into a channel slice of its
@@ -320,6 +321,67 @@ def synthetic_weights(seed: int = 0, bias_std: float = 0.02) -> Dict[str, torch.
         if name.endswith(".cv2") and ".csp.b" in name:
             w[name[:-4] + ".alpha"] = torch.tensor(0.5)
     return w
+
+
+# ------------------------------------------------------------------------------------------ re-parameterisation
+BN_EPS = 1e-6  # yolo_heads_l_arch_params.yaml:139
+
+
+def _bn_scale_shift(sd: Dict[str, torch.Tensor], prefix: str, eps: float = BN_EPS):
+    s = sd[prefix + ".weight"].double() / torch.sqrt(sd[prefix + ".running_var"].double() + eps)
+    return s, sd[prefix + ".bias"].double() - sd[prefix + ".running_mean"].double() * s
+
+
+def fold_conv_bn(sd: Dict[str, torch.Tensor], name: str, eps: float = BN_EPS):
+    """Conv(bias=False)+BN (+ReLU) -> conv weight/bias.  Keys: `{name}.conv.weight`, `{name}.bn.*`."""
+    s, t = _bn_scale_shift(sd, name + ".bn", eps)
+    return (sd[name + ".conv.weight"].double() * s[:, None, None, None]).float(), t.float()
+
+
+def fold_qarepvgg(sd: Dict[str, torch.Tensor], name: str, eps: float = BN_EPS):
+    """QARepVGG block -> one 3x3 conv + bias:
+    W = post_bn( bn3(W3) + alpha * pad(W1) + I ),  b likewise.  Keys: `{name}.conv3.weight`, `{name}.bn3.*`,
+    `{name}.conv1.weight/.bias`, optional `{name}.alpha`, `{name}.post_bn.*`; the identity branch exists iff
+    the block is square with stride 1 and `{name}.residual` (bool tensor / flag) is true or absent-but-square."""
+    w3 = sd[name + ".conv3.weight"].double()
+    s3, t3 = _bn_scale_shift(sd, name + ".bn3", eps)
+    alpha = sd[name + ".alpha"].double() if (name + ".alpha") in sd else torch.tensor(1.0, dtype=torch.float64)
+    w = w3 * s3[:, None, None, None] + alpha * torch.nn.functional.pad(sd[name + ".conv1.weight"].double(), [1, 1, 1, 1])
+    b = t3 + alpha * sd[name + ".conv1.bias"].double()
+    residual = bool(sd[name + ".residual"]) if (name + ".residual") in sd else False
+    if residual:
+        assert w.shape[0] == w.shape[1], "identity branch needs a square block"
+        idx = torch.arange(w.shape[0])
+        w[idx, idx, 1, 1] += 1.0
+    sp, tp = _bn_scale_shift(sd, name + ".post_bn", eps)
+    return (w * sp[:, None, None, None]).float(), (b * sp + tp).float()
+
+
+def deploy_from_unfused(sd: Dict[str, torch.Tensor], eps: float = BN_EPS) -> Dict[str, torch.Tensor]:
+    """As-trained tensors (per layer name of `conv_names()`) -> the deploy-form dict `pack()` takes.
+    A layer may be given as a QARepVGG block (`{name}.conv3.weight` ...), a Conv-BN (`{name}.conv.weight` +
+    `{name}.bn.*`) or an already plain conv (`{name}.w` / `{name}.b`, or torch style `{name}.weight/.bias`).
+    Mapping super_gradients' own state_dict keys onto these names is the remaining step of SURVEY 8 f3
+    (super_gradients is not available offline to verify key names against)."""
+    out: Dict[str, torch.Tensor] = {}
+    for name, k, cin, cout, tr in conv_names():
+        if name + ".conv3.weight" in sd:
+            out[name + ".w"], out[name + ".b"] = fold_qarepvgg(sd, name, eps)
+        elif name + ".conv.weight" in sd:
+            out[name + ".w"], out[name + ".b"] = fold_conv_bn(sd, name, eps)
+        elif name + ".w" in sd:
+            out[name + ".w"], out[name + ".b"] = sd[name + ".w"].float(), sd[name + ".b"].float()
+        elif name + ".weight" in sd:
+            out[name + ".w"], out[name + ".b"] = sd[name + ".weight"].float(), sd[name + ".bias"].float()
+        else:
+            raise KeyError(f"no tensors for layer {name!r}")
+        exp = (cin, cout, 2, 2) if tr else (cout, cin, k, k)
+        if tuple(out[name + ".w"].shape) != exp:
+            raise ValueError(f"{name}: weight shape {tuple(out[name + '.w'].shape)} != {exp}")
+        if name.endswith(".cv2") and ".csp.b" in name:
+            a = name[:-4] + ".alpha"
+            out[a] = sd[a].float().reshape(()) if a in sd else torch.tensor(1.0)
+    return out
 
 
 def total_macs(image_size: int = 640) -> int:

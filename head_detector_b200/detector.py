@@ -109,6 +109,23 @@ class HeadDetector:
                                       flame_params=fp, vertices_3d=verts[i], head_pose=poses[i]))
         return heads
 
+    def predict_batch(self, images: List[Any], confidence_threshold: float = 0.5) -> List[PredictionResult]:
+        """Batched `__call__` (extension; semantics of yolo_heads_post_prediction_callback.py:55-97: every image
+        independently).  `len(images)` must not exceed the `batch_size` the detector was built with; the
+        batch is padded with copies of the last image."""
+        if not 0 < len(images) <= self._batch:
+            raise ValueError(f"predict_batch takes 1..{self._batch} images, got {len(images)}")
+        originals = [self._convert_image(im) for im in images]
+        prepared = [self._transform_image(o) for o in originals]
+        while len(prepared) < self._batch:
+            prepared.append(prepared[-1])
+        batch = torch.from_numpy(np.stack([p[0] for p in prepared])).to(self._device)
+        xf = torch.tensor([[p[1][0], p[1][1], p[2]] for p in prepared], dtype=torch.float32)
+        out = self.detect_batch(batch, confidence_threshold, xf)
+        out = {k: v.cpu() if k in ("offsets", "keep_cnt") else v for k, v in out.items()}
+        return [PredictionResult(original_image=o, heads=self._parse_predictions(out, i, {"padding": p[1], "scale": p[2]}))
+                for i, (o, p) in enumerate(zip(originals, prepared))]
+
     def __call__(self, image, confidence_threshold: float = 0.5) -> PredictionResult:
         original = self._convert_image(image)
         img, padding, scale = self._transform_image(original)

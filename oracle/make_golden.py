@@ -121,6 +121,14 @@ def main():
         rpy=np.array([[h.head_pose.roll, h.head_pose.pitch, h.head_pose.yaw] for h in res], dtype=np.float64),
         out_scale=np.array([float(h.flame_params.scale) for h in res]),
     )
+    # --- 5. reference letterbox (detector.py:40-52) on a non-square image: checksum + geometry ------
+    import hashlib
+    rng = np.random.default_rng(17)
+    src = rng.integers(0, 256, (375, 500, 3), dtype=np.uint8)
+    t, pad, scale = det._transform_image(src)          # float [1,3,640,640] in [0,1]
+    u8 = (t[0].permute(1, 2, 0) * 255.0).round().to(torch.uint8).numpy()
+    np.savez_compressed(os.path.join(OUT, "letterbox_ref.npz"), sha1=np.frombuffer(hashlib.sha1(u8.tobytes()).digest(), dtype=np.uint8),
+                        pad=np.array(pad), scale=np.array(scale), probe=u8[::37, ::41].copy(), seed=np.array(17), shape=np.array(src.shape))
     print("golden fixtures written to", OUT)
 
 

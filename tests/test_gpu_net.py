@@ -249,3 +249,50 @@ def test_two_detector_handles_run_concurrently():
         assert n == ref[0] > 0
         assert torch.equal(e.keep_idx, ref[1]) and torch.equal(e.head_params(n), ref[2])
         assert torch.equal(e.head_verts(n), ref[3]) and torch.equal(e.boxes, ref[4])
+
+
+def test_parse_predictions_matches_reference_golden(golden_dir):
+    """Host glue of `HeadDetector` (detector.py:61-90) on the reference's own output for the same kept
+    heads: integer bboxes equal, vertices within 1e-4/scale, roll/pitch/yaw and rescaled `scale` equal."""
+    import os
+
+    from head_detector_b200.detector import HeadDetector
+    from head_detector_b200.flame import FLAMELayer
+
+    g = np.load(os.path.join(golden_dir, "parse_ref.npz"))
+    flame = FLAMELayer()
+    params = torch.from_numpy(g["params"]).cuda()
+    n = params.shape[0]
+    pad, scale = (0, 80), 0.5
+    xf = torch.tensor([[pad[0], pad[1], scale]] * n).cuda()
+    _, rot, verts = flame.decode(params, xform=xf, live=(128, 64))
+    out = {"offsets": torch.tensor([0, n], dtype=torch.int32), "keep_boxes": torch.from_numpy(g["boxes"])[None].cuda(),
+           "keep_scores": torch.from_numpy(g["scores"])[None].cuda(), "vertices": verts, "params": params, "rotations": rot}
+    det = object.__new__(HeadDetector)
+    det._image_size = 640
+    heads = det._parse_predictions(out, 0, {"padding": pad, "scale": scale})
+    assert [[int(v) for v in h.bbox] for h in heads] == g["bbox_xywh"].tolist()
+    assert np.abs(np.stack([h.vertices_3d for h in heads]) - g["vertices_3d"]).max() < 1e-4 / scale
+    assert np.allclose([[h.head_pose.roll, h.head_pose.pitch, h.head_pose.yaw] for h in heads], g["rpy"], atol=1e-3)
+    assert np.allclose([float(h.flame_params.scale) for h in heads], g["out_scale"], rtol=1e-6)
+    assert np.allclose([float(h.score) for h in heads], g["scores"])
+
+
+def test_predict_batch_api():
+    """Batched extension of the public call: one PredictionResult per image, per-image letterbox."""
+    import head_detector_b200
+    from head_detector_b200 import synth
+
+    det = head_detector_b200.HeadDetector(weights=no.synthetic_weights(0), batch_size=3)
+    boxes, scores = synth.engineered_heads(3, 8400, 640, heads=4, per_cluster=8, seed=2)
+    det.model.set_override(boxes.cuda(), scores.cuda())
+    rng = np.random.default_rng(1)
+    images = [rng.integers(0, 256, (640, 640, 3), dtype=np.uint8), rng.integers(0, 256, (320, 480, 3), dtype=np.uint8)]
+    res = det.predict_batch(images)
+    assert len(res) == 2
+    for b, r in enumerate(res):
+        want = nms_oracle.select_nms(boxes[b].numpy(), scores[b].numpy())
+        assert len(r.heads) == len(want) > 0 and r.original_image.shape == images[b].shape
+        assert all(h.vertices_3d.shape == (5023, 3) for h in r.heads)
+    with pytest.raises(ValueError):
+        det.predict_batch([images[0]] * 4)

@@ -40,3 +40,21 @@ def test_rot6d_matches_oracle_and_rpy_matches_reference(golden_dir):
 
 def test_limit_angle():
     assert limit_angle(190.0) == -170.0 and limit_angle(-190.0) == 170.0 and limit_angle(10.0) == 10.0
+
+
+def test_letterbox_matches_reference(golden_dir):
+    """`_transform_image` (reference detector.py:40-52: Lanczos4 resize, centred pad 127) - same pixels,
+    same padding / scale bookkeeping as the unmodified reference run in the build container."""
+    import hashlib
+
+    from head_detector_b200.detector import HeadDetector
+
+    g = np.load(os.path.join(golden_dir, "letterbox_ref.npz"))
+    det = object.__new__(HeadDetector)
+    det._image_size = 640
+    src = np.random.default_rng(int(g["seed"])).integers(0, 256, tuple(g["shape"]), dtype=np.uint8)
+    img, pad, scale = det._transform_image(src)
+    assert img.shape == (640, 640, 3) and img.dtype == np.uint8
+    assert tuple(pad) == tuple(g["pad"]) and abs(scale - float(g["scale"])) < 1e-12
+    assert np.array_equal(img[::37, ::41], g["probe"])
+    assert np.array_equal(np.frombuffer(hashlib.sha1(img.tobytes()).digest(), dtype=np.uint8), g["sha1"])

@@ -77,3 +77,37 @@ def test_decode_channel_rotation():
     assert fl[0, 1, 409].item() == 1.5 * 8 and fl[0, 2, 410].item() == 1.5 * 8
     assert abs(scores[0, 0, 0].item() - 0.5) < 1e-7
     assert torch.allclose(boxes[0, 0], torch.tensor([0.5 - 8, 0.5 - 8, 0.5 + 8, 0.5 + 8]) * 8)
+
+
+def test_product_fold_matches_oracle_fold_and_unfused_forward():
+    """arch.fold_qarepvgg / fold_conv_bn / deploy_from_unfused (what a real checkpoint goes through)
+    against the oracle's unfused blocks."""
+    g = torch.Generator().manual_seed(4)
+    for cin, cout, stride, residual, alpha in [(16, 16, 1, True, False), (8, 24, 2, False, False), (12, 12, 1, False, True)]:
+        m = no.QARepVGGUnfused(cin, cout, stride, residual, alpha).eval()
+        for bn in (m.bn3, m.post_bn):
+            no.randomize_bn_(bn, g)
+        sd = {"blk." + k: v.detach() for k, v in m.state_dict().items()}
+        sd["blk.residual"] = torch.tensor(m.residual)
+        w, b = arch.fold_qarepvgg(sd, "blk")
+        ow, ob = no.fold_qarepvgg(m)
+        assert torch.allclose(w, ow, atol=1e-6) and torch.allclose(b, ob, atol=1e-6)
+        x = torch.randn(1, cin, 9, 9, generator=g)
+        with torch.no_grad():
+            assert (m(x) - torch.relu(torch.nn.functional.conv2d(x, w, b, stride=stride, padding=1))).abs().max() < 1e-4
+    bn = torch.nn.BatchNorm2d(6, eps=1e-6).eval()
+    no.randomize_bn_(bn, g)
+    conv_w = torch.randn(6, 4, 1, 1, generator=g)
+    sd = {"c.conv.weight": conv_w, **{"c.bn." + k: v for k, v in bn.state_dict().items()}}
+    w, b = arch.fold_conv_bn(sd, "c")
+    ow, ob = no.fold_conv_bn(conv_w, bn)
+    assert torch.allclose(w, ow.detach(), atol=1e-6) and torch.allclose(b, ob.detach(), atol=1e-6)
+    # whole-network plumbing: plain tensors pass through, shapes are checked
+    dw = no.synthetic_weights(1)
+    out = arch.deploy_from_unfused(dw)
+    assert set(out) == set(dw) and all(torch.equal(out[k], dw[k].float()) for k in dw if k.endswith(".w"))
+    bad = dict(dw)
+    bad["stem.w"] = torch.zeros(48, 3, 5, 5)
+    import pytest
+    with pytest.raises(ValueError):
+        arch.deploy_from_unfused(bad)
