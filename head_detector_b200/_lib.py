@@ -54,6 +54,7 @@ _SIGS = {
                                    C.c_void_p, C.c_void_p]),
     "vgh_select_nms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vgh_letterbox": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vgh_detector_create": (C.c_int, [C.POINTER(NetDesc), C.c_void_p, C.POINTER(C.c_void_p)]),
     "vgh_detector_destroy": (None, [C.c_void_p]),
     "vgh_detector_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -13,6 +13,7 @@
 #include "aux_kernels.cuh"
 #include "conv_igemm.cuh"
 #include "flame_decode.cuh"
+#include "letterbox.cuh"
 #include "select_nms.cuh"
 
 using namespace vgh;
@@ -72,6 +73,17 @@ extern "C" int vgh_select_nms(const float* boxes_dev, const float* scores_dev, i
   if (B < 0 || A <= 0) return fail(1, "bad batch/anchor count");
   return select_nms_launch(boxes_dev, scores_dev, B, A, conf_thr, iou_thr, top_k, keep_k, keep_idx_dev, keep_cnt_dev,
                            keep_boxes_dev, keep_scores_dev, static_cast<cudaStream_t>(stream), g_err, sizeof(g_err));
+}
+
+// ------------------------------------------------------------------------------------------ letterbox
+extern "C" int vgh_letterbox(const uint8_t* src_dev, const int64_t* offsets, const int32_t* heights, const int32_t* widths,
+                             int n, int image_size, uint8_t* out_dev, float* xform_host, void* stream) {
+  if (n < 0) return fail(1, "negative image count");
+  if (n == 0) return 0;
+  if (!src_dev || !offsets || !heights || !widths || !out_dev) return fail(1, "null argument");
+  if (image_size < 1) return fail(1, "bad image size");
+  return letterbox_launch(src_dev, offsets, heights, widths, n, image_size, out_dev, xform_host,
+                          static_cast<cudaStream_t>(stream), g_err, sizeof(g_err));
 }
 
 // ------------------------------------------------------------------------------------------ detector

@@ -6,7 +6,9 @@
 
 Differences that are extensions, not changes: `weights=` (a deploy-form weight dict or a path to a
 torch-saved one; the HF download of detector.py:25-30 is impossible offline), `batch_size=` and
-`detect_batch()` (batched semantics of yolo_heads_post_prediction_callback.py:55-97)."""
+`detect_batch()` (batched semantics of yolo_heads_post_prediction_callback.py:55-97), and
+`device_letterbox=` (default True: `_transform_image` runs as one CUDA kernel for the whole batch,
+bit-exact with the cv2 calls of detector.py:47-50; False keeps the reference's host cv2 path)."""
 import os
 import warnings
 from typing import Any, Dict, List, Optional, Tuple, Union
@@ -19,12 +21,13 @@ from .detection_result import PredictionResult
 from .engine import Engine
 from .flame import FLAMELayer
 from .head_info import Bbox, FlameParams, HeadMetadata
+from .preprocess import letterbox_batch, letterbox_geometry
 from .utils import rpy_from_rotations
 
 
 class HeadDetector:
     def __init__(self, model: str = "vgg_heads_l", image_size: int = 640, weights: Union[None, str, Dict[str, torch.Tensor]] = None,
-                 batch_size: int = 1, keep_top_k: int = 100):
+                 batch_size: int = 1, keep_top_k: int = 100, device_letterbox: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("head_detector_b200.HeadDetector needs a CUDA device (sm_100a); there is no CPU fallback")
         self._image_size = image_size
@@ -32,6 +35,7 @@ class HeadDetector:
         self._flame = FLAMELayer()
         self._batch = batch_size
         self._keep_top_k = keep_top_k
+        self._device_letterbox = device_letterbox
         self.model = self._read_model(model, weights)
 
     def _read_model(self, model: str, weights=None) -> Engine:
@@ -116,23 +120,35 @@ class HeadDetector:
         if not 0 < len(images) <= self._batch:
             raise ValueError(f"predict_batch takes 1..{self._batch} images, got {len(images)}")
         originals = [self._convert_image(im) for im in images]
+        batch, xf, caches = self._prepare_batch(originals)
+        out = self.detect_batch(batch, confidence_threshold, xf)
+        out = {k: v.cpu() if k in ("offsets", "keep_cnt") else v for k, v in out.items()}
+        return [PredictionResult(original_image=o, heads=self._parse_predictions(out, i, c))
+                for i, (o, c) in enumerate(zip(originals, caches))]
+
+    def _prepare_batch(self, originals: List[np.ndarray]):
+        """`_preprocess` (detector.py:54-56) for up to batch_size images: letterboxed uint8 cuda batch
+        [batch_size,S,S,3] (padded with copies of the last image), xform [batch_size,3], per-image caches."""
+        S, n = self._image_size, len(originals)
+        if self._device_letterbox:
+            frames = torch.empty(self._batch, S, S, 3, dtype=torch.uint8, device=self._device)
+            _, xf = letterbox_batch(originals, S, out=frames)
+            if n < self._batch:
+                frames[n:] = frames[n - 1]
+                xf = torch.cat([xf, xf[-1:].expand(self._batch - n, 3)])
+            geo = [letterbox_geometry(o.shape[0], o.shape[1], S) for o in originals]
+            return frames, xf, [{"padding": g[1], "scale": g[2]} for g in geo]
         prepared = [self._transform_image(o) for o in originals]
+        caches = [{"padding": p[1], "scale": p[2]} for p in prepared]
         while len(prepared) < self._batch:
             prepared.append(prepared[-1])
         batch = torch.from_numpy(np.stack([p[0] for p in prepared])).to(self._device)
         xf = torch.tensor([[p[1][0], p[1][1], p[2]] for p in prepared], dtype=torch.float32)
-        out = self.detect_batch(batch, confidence_threshold, xf)
-        out = {k: v.cpu() if k in ("offsets", "keep_cnt") else v for k, v in out.items()}
-        return [PredictionResult(original_image=o, heads=self._parse_predictions(out, i, {"padding": p[1], "scale": p[2]}))
-                for i, (o, p) in enumerate(zip(originals, prepared))]
+        return batch, xf, caches
 
     def __call__(self, image, confidence_threshold: float = 0.5) -> PredictionResult:
         original = self._convert_image(image)
-        img, padding, scale = self._transform_image(original)
-        batch = torch.from_numpy(img)[None].to(self._device)
-        if self._batch != 1:
-            batch = batch.expand(self._batch, -1, -1, -1).contiguous()
-        xf = torch.tensor([[padding[0], padding[1], scale]] * self._batch, dtype=torch.float32)
+        batch, xf, caches = self._prepare_batch([original])
         out = self.detect_batch(batch, confidence_threshold, xf)
-        heads = self._parse_predictions(out, 0, {"padding": padding, "scale": scale})
+        heads = self._parse_predictions(out, 0, caches[0])
         return PredictionResult(original_image=original, heads=heads)

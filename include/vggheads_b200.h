@@ -4,6 +4,8 @@
  * (SURVEY.md 8b).  Each entry point below names the reference interface it replaces so a
  * maintainer can bind it from head_detector/detector.py (see INTEGRATION.md for the ctypes stub):
  *
+ *   vgh_letterbox             <- `HeadDetector._transform_image` head_detector/detector.py:40-52
+ *                                (cv2.resize INTER_LANCZOS4 + cv2.copyMakeBorder, bit-exact)
  *   vgh_detector_forward      <- `self.model(image)`            head_detector/detector.py:58-59
  *                                (TorchScript YoloHeads_L: yolo_head_training/yolo_head/
  *                                 yolo_head_ndfl_heads.py:117-175, yolo_head_dfl_head.py:141-186)
@@ -64,6 +66,21 @@ int vgh_flame_decode(const vgh_flame* f, const float* params_dev, int n, int n_s
 int vgh_select_nms(const float* boxes_dev, const float* scores_dev, int B, int A, float conf_thr, float iou_thr,
                    int top_k, int keep_k, int32_t* keep_idx_dev, int32_t* keep_cnt_dev, float* keep_boxes_dev,
                    float* keep_scores_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------- letterbox */
+/* HeadDetector._transform_image (detector.py:40-52) for n RGB uint8 images of different sizes in one
+ * launch.  src_dev: the images packed back to back in DEVICE memory, image i starting at byte
+ * offsets[i] as [heights[i], widths[i], 3] (no row padding).  offsets / heights / widths are HOST
+ * arrays.  Per image: new size = longest side -> image_size with the reference's int() truncation
+ * (detector.py:42-45), OpenCV's fixed-point 8-tap Lanczos-4 resize (bit-exact, border replicated),
+ * centred in the square (pad_w//2 left, pad_h//2 top) on a border of (127,0,0) - what cv2.copyMakeBorder
+ * makes of the reference's scalar `value=127`.  out_dev: uint8
+ * [n,image_size,image_size,3], directly consumable by vgh_detector_forward.  xform_host (optional,
+ * HOST) [n,3] = (pad_x, pad_y, scale) with scale = image_size / max(h, w) - the `cache` of
+ * detector.py:52-56, in the layout vgh_detector_postprocess takes.  An image whose resized extent
+ * would be empty (cv2.resize raises there) fails with a non-zero status. */
+int vgh_letterbox(const uint8_t* src_dev, const int64_t* offsets, const int32_t* heights, const int32_t* widths, int n,
+                  int image_size, uint8_t* out_dev, float* xform_host, void* stream);
 
 /* ---------------------------------------------------------------------------------- conv network */
 /* Execution plan of the deploy-form network, produced by head_detector_b200/arch.py from the

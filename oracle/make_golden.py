@@ -13,6 +13,9 @@ Fixtures written (all small, committed):
   nms_ref_cases.npz      reference `utils.nms` (utils.py:159-194) on seeded anchors, with the
                          surviving ORIGINAL anchor ids recovered through an index column
   parse_ref.npz          reference `HeadDetector._parse_predictions` (detector.py:61-90)
+  letterbox_ref.npz      reference `HeadDetector._transform_image` (detector.py:40-52), one shape
+  letterbox_ref_cases.npz  the same on seven more shapes (up/down-scaling, tall, wide, identity);
+                         `python oracle/make_golden.py --only-letterbox` rewrites just this file
 """
 import json
 import os
@@ -64,7 +67,35 @@ def clustered_anchors(n_anchor: int, n_clusters: int, per_cluster: int, seed: in
     return boxes.float(), scores.float()
 
 
+LETTERBOX_SHAPES = ((720, 1280), (1280, 720), (640, 640), (200, 150), (1080, 1920), (333, 1000), (641, 640))
+
+
+def letterbox_cases():
+    """Unmodified reference `_transform_image` (detector.py:40-52) on seeded images of several shapes:
+    sha1 of the letterboxed uint8 frame, a strided probe of it, padding and scale."""
+    import hashlib
+
+    from head_detector.detector import HeadDetector
+
+    det = object.__new__(HeadDetector)
+    det._image_size, det._device = 640, torch.device("cpu")
+    out = {"shapes": np.array(LETTERBOX_SHAPES), "seed0": np.array(100)}
+    for i, (h, w) in enumerate(LETTERBOX_SHAPES):
+        src = np.random.default_rng(100 + i).integers(0, 256, (h, w, 3), dtype=np.uint8)
+        t, pad, scale = det._transform_image(src)
+        u8 = (t[0].permute(1, 2, 0) * 255.0).round().to(torch.uint8).numpy()
+        out[f"sha1_{i}"] = np.frombuffer(hashlib.sha1(u8.tobytes()).digest(), dtype=np.uint8)
+        out[f"probe_{i}"] = u8[::53, ::47].copy()
+        out[f"pad_{i}"] = np.array(pad)
+        out[f"scale_{i}"] = np.array(scale)
+        print("letterbox", (h, w), "pad", pad, "scale", scale)
+    np.savez_compressed(os.path.join(OUT, "letterbox_ref_cases.npz"), **out)
+
+
 def main():
+    if "--only-letterbox" in sys.argv:
+        letterbox_cases()
+        return
     os.makedirs(OUT, exist_ok=True)
     from head_detector.flame import FLAMELayer, reproject_spatial_vertices  # the reference, unmodified
     from head_detector.head_info import FlameParams
@@ -129,6 +160,7 @@ def main():
     u8 = (t[0].permute(1, 2, 0) * 255.0).round().to(torch.uint8).numpy()
     np.savez_compressed(os.path.join(OUT, "letterbox_ref.npz"), sha1=np.frombuffer(hashlib.sha1(u8.tobytes()).digest(), dtype=np.uint8),
                         pad=np.array(pad), scale=np.array(scale), probe=u8[::37, ::41].copy(), seed=np.array(17), shape=np.array(src.shape))
+    letterbox_cases()
     print("golden fixtures written to", OUT)
 
 
