@@ -43,6 +43,8 @@ struct ConvLaunch {
   int ks;                        // swapped kernel: k-blocks per pipeline stage (must divide taps*cin/BK)
   int ngroups, gw;               // swapped kernel: output-channel groups and channels per group (<= 128)
   int stg_bufs;                  // swapped kernel: epilogue staging tiles (2 = store of item i overlaps item i+1)
+  int xr, xslots;                // swapped kernel, 3x3 stride 1: pixel tile + halo rows fetched once per column shift
+                                 // and reused by the three row taps (xslots = pixel-tile ring depth; `stages` = weight ring)
   int acc_stages, n_tiles, num_items;  // TMEM accumulator stages (1|2), N tiles, work items (persistent CTAs)
 };
 

@@ -16,6 +16,17 @@
 // group; the groups of one tile run on neighbouring CTAs at the same time, so the pixel tile is read
 // from HBM once).  fp32 outputs (raw head tensors) use the same path with a 4-byte staging tile.
 //
+// XR variant (3x3 stride-1 layers, `p.xr`): the nine taps of a 3x3 filter read nine overlapping pixel
+// tiles; fetched tap by tap that is 9x the unique L2->SM traffic of the tile, and with Cout <= 128 per
+// group that traffic - not the tensor pipe - bounds the layer (~6-7 TB/s of distinct pixel bytes,
+// profiles/r1_final_ncu_*).  Here the pixel tile is fetched ONCE per column shift dx with a one-row
+// halo above and below ([BK, tw, th+2] box, OOB rows/columns zero-filled = padding) and the three
+// row taps dy = 0,1,2 are three MMAs whose pixel-operand descriptor starts dy*tw rows further down
+// the same shared-memory tile.  With tw a multiple of 8 that offset is a whole number of 8-row swizzle
+// atoms, so the descriptors stay canonical.  3*(th+2) tile rows instead of 9*th: 2.4-2.7x less pixel
+// traffic.  Weights (identical for every CTA, coalesced in L2) keep streaming tap by tap through their
+// own, deeper ring; the pixel ring has 2-3 slots.  K order: (cin block, dx, dy).
+//
 // Everything else matches conv_igemm.cu: persistent CTAs, TMA (4-D pixel box with OOB zero fill =
 // padding, traversal stride = conv stride; 2-D weight box), mbarrier ring, double-buffered TMEM.
 #include <cstdio>
@@ -28,19 +39,21 @@ namespace vgh {
 constexpr int kSwapEpiWarps = 8;
 constexpr int kSwapThreads = 64 + 32 * kSwapEpiWarps;
 
-template <int BK>
+template <int BK, bool XR>
 __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const __grid_constant__ ConvLaunch p) {
   constexpr uint32_t kRowBytes = BK * 2;
   constexpr uint32_t kWBytes = 128 * kRowBytes;  // weight tile: 128 cout rows
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int npix = p.tw * p.th;                                   // UMMA N (multiple of 16, <= 256)
-  const uint32_t x_bytes = static_cast<uint32_t>(npix) * kRowBytes;  // pixel tile bytes
+  // pixel tile bytes; XR: the tile carries one halo row above and below
+  const uint32_t x_bytes = static_cast<uint32_t>(XR ? p.tw * (p.th + 2) : npix) * kRowBytes;
   const uint32_t x_slot = (x_bytes + 1023u) & ~1023u;
-  const int ks = p.ks;                                              // k-blocks per pipeline stage (one barrier round trip)
+  const int ks = XR ? 1 : p.ks;                                     // k-blocks per pipeline stage (one barrier round trip)
+  const int x_slots = XR ? p.xslots : p.stages * ks;               // XR: the pixel tiles have their own (shallower) ring
   const uint32_t w_base = smem_base;
   const uint32_t x_base = w_base + p.stages * ks * kWBytes;
-  const uint32_t stage_base = x_base + p.stages * ks * x_slot;             // epilogue tile [npix][n_total] bf16
+  const uint32_t stage_base = x_base + x_slots * x_slot;                   // epilogue tile [npix][n_total] bf16
   const int gw = p.gw;                                                     // channels per group (<= 128)
   const uint32_t esz = p.out_fp32 ? 4u : 2u;
   const uint32_t stage_bytes = static_cast<uint32_t>(npix * gw) * esz;
@@ -52,7 +65,9 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
   const uint32_t tmem_full_bar = bar_base + 16 * p.stages;
   const uint32_t tmem_empty_bar = tmem_full_bar + 16;
   const uint32_t res_full_bar = tmem_empty_bar + 16;  // [2]
-  const uint32_t tmem_slot = res_full_bar + 16;
+  const uint32_t xfull_bar = res_full_bar + 16;       // [8]  XR: pixel-tile ring
+  const uint32_t xempty_bar = xfull_bar + 64;         // [8]
+  const uint32_t tmem_slot = xempty_bar + 64;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -71,6 +86,12 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
     }
     mbar_init(res_full_bar, 1);
     mbar_init(res_full_bar + 8, 1);
+    if (XR) {
+      for (int s = 0; s < p.xslots; ++s) {
+        mbar_init(xfull_bar + 8 * s, 1);
+        mbar_init(xempty_bar + 8 * s, 1);
+      }
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -94,8 +115,8 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
     if (lane == 0) {
       // ===================== TMA producer =====================
       const uint32_t tx_bytes = kWBytes + x_bytes;
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, xs = 0;
+      uint32_t phase = 0, xphase = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
         const int tile = item / p.ngroups;
         const int n_base = (item - tile * p.ngroups) * gw;
@@ -103,6 +124,30 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
         const int t_in = tile - b_img * tiles_per_img;
         const int tyi = t_in / p.tiles_x;
         const int h0 = tyi * p.th, w0 = (t_in - tyi * p.tiles_x) * p.tw;
+        if constexpr (XR) {
+          // pixel tile (with halo rows) once per (cin block, dx); weights tap by tap
+          for (int cb = 0; cb < cblks; ++cb) {
+            for (int dx = 0; dx < 3; ++dx) {
+              mbar_wait(xempty_bar + 8 * xs, xphase ^ 1);
+              mbar_arrive_expect_tx(xfull_bar + 8 * xs, x_bytes);
+              tma_load_4d(x_base + xs * x_slot, &p.tmA, xfull_bar + 8 * xs, p.cin_off + cb * BK, w0 + dx - 1, h0 - 1, b_img);
+              if (++xs == p.xslots) {
+                xs = 0;
+                xphase ^= 1;
+              }
+              for (int dy = 0; dy < 3; ++dy) {
+                mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                mbar_arrive_expect_tx(full_bar + 8 * stage, kWBytes);
+                tma_load_2d(w_base + stage * kWBytes, &p.tmB, full_bar + 8 * stage, (dy * 3 + dx) * p.cin + cb * BK, n_base);
+                if (++stage == p.stages) {
+                  stage = 0;
+                  phase ^= 1;
+                }
+              }
+            }
+          }
+          continue;
+        }
         int tap = 0, cb = 0;
         for (int kb = 0; kb < num_kb; kb += ks) {
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
@@ -130,14 +175,49 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
     if (lane == 0) {
       // ===================== MMA issuer =====================
       const uint32_t idesc = umma_idesc_bf16(128, static_cast<uint32_t>(npix));
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, xs = 0;
+      uint32_t phase = 0, xphase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
         mbar_wait(tmem_empty_bar + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d = tmem_acc + acc * acc_cols;
+        if constexpr (XR) {
+          uint32_t accumulate = 0;
+          const uint32_t dy_bytes = static_cast<uint32_t>(p.tw) * kRowBytes;  // one tile row; tw % 8 == 0: whole swizzle atoms
+          for (int g = 0; g < 3 * cblks; ++g) {
+            mbar_wait(xfull_bar + 8 * xs, xphase);
+            tc_fence_after();
+            for (int dy = 0; dy < 3; ++dy) {
+              mbar_wait(full_bar + 8 * stage, phase);
+              tc_fence_after();
+              const uint64_t w_desc = umma_smem_desc(w_base + stage * kWBytes, kRowBytes);
+              const uint64_t x_desc = umma_smem_desc(x_base + xs * x_slot + dy * dy_bytes, kRowBytes);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                umma_bf16(d, w_desc + 2 * k, x_desc + 2 * k, idesc, accumulate);
+                accumulate = 1u;
+              }
+              umma_commit(empty_bar + 8 * stage);
+              if (++stage == p.stages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+            umma_commit(xempty_bar + 8 * xs);  // all three row taps of this pixel tile have been issued
+            if (++xs == p.xslots) {
+              xs = 0;
+              xphase ^= 1;
+            }
+          }
+          umma_commit(tmem_full_bar + 8 * acc);
+          if (++acc == p.acc_stages) {
+            acc = 0;
+            acc_phase ^= 1;
+          }
+          continue;
+        }
         for (int kb = 0; kb < num_kb; kb += ks) {
           mbar_wait(full_bar + 8 * stage, phase);
           tc_fence_after();
@@ -268,17 +348,21 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
 }
 
 size_t conv_swap_smem_bytes(const ConvLaunch& L, int bk) {
-  const size_t x_slot = (static_cast<size_t>(L.tw * L.th) * bk * 2 + 1023) & ~static_cast<size_t>(1023);
   const size_t staging = (static_cast<size_t>(L.tw * L.th) * L.gw * (L.out_fp32 ? 4 : 2) + 1023) & ~static_cast<size_t>(1023);
-  return 1024 + static_cast<size_t>(L.stages) * L.ks * (128 * bk * 2 + x_slot) + L.stg_bufs * staging + 16 * L.stages + 128;
+  if (L.xr) {
+    const size_t x_slot = (static_cast<size_t>(L.tw * (L.th + 2)) * bk * 2 + 1023) & ~static_cast<size_t>(1023);
+    return 1024 + static_cast<size_t>(L.stages) * 128 * bk * 2 + L.xslots * x_slot + L.stg_bufs * staging + 16 * L.stages + 256;
+  }
+  const size_t x_slot = (static_cast<size_t>(L.tw * L.th) * bk * 2 + 1023) & ~static_cast<size_t>(1023);
+  return 1024 + static_cast<size_t>(L.stages) * L.ks * (128 * bk * 2 + x_slot) + L.stg_bufs * staging + 16 * L.stages + 256;
 }
 
-template <int BK>
+template <int BK, bool XR>
 static int launch_swap_t(const ConvLaunch& L, int sms, cudaStream_t stream, char* err, size_t errlen) {
   static size_t configured = 0;
   const size_t smem = conv_swap_smem_bytes(L, BK);
   if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_swap_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_swap_kernel<BK, XR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       snprintf(err, errlen, "swap conv: set smem %zu failed: %s", smem, cudaGetErrorString(e));
       return 4;
@@ -295,7 +379,7 @@ static int launch_swap_t(const ConvLaunch& L, int sms, cudaStream_t stream, char
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = conv_pdl_enabled() ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm_swap_kernel<BK>, L);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm_swap_kernel<BK, XR>, L);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(err, errlen, "swap conv launch failed: %s", cudaGetErrorString(e));
@@ -305,8 +389,17 @@ static int launch_swap_t(const ConvLaunch& L, int sms, cudaStream_t stream, char
 }
 
 int conv_swap_launch(const ConvLaunch& L, int bk, int sms, cudaStream_t stream, char* err, size_t errlen) {
-  if (bk == 64) return launch_swap_t<64>(L, sms, stream, err, errlen);
-  if (bk == 32) return launch_swap_t<32>(L, sms, stream, err, errlen);
+  if (L.xr) {
+    if (L.ntaps != 9 || L.stride != 1 || L.tw % 8 || L.xslots < 2 || L.xslots > 8 || L.stages < 2) {
+      snprintf(err, errlen, "swap conv: launch not eligible for the tap-reuse variant (taps %d stride %d tile %dx%d xslots %d stages %d)",
+               L.ntaps, L.stride, L.tw, L.th, L.xslots, L.stages);
+      return 7;
+    }
+    if (bk == 64) return launch_swap_t<64, true>(L, sms, stream, err, errlen);
+    if (bk == 32) return launch_swap_t<32, true>(L, sms, stream, err, errlen);
+  }
+  if (bk == 64) return launch_swap_t<64, false>(L, sms, stream, err, errlen);
+  if (bk == 32) return launch_swap_t<32, false>(L, sms, stream, err, errlen);
   snprintf(err, errlen, "unsupported BK %d", bk);
   return 6;
 }

@@ -95,6 +95,7 @@ struct OpRt {
   int cfg_swap = -1;                                          // -1 = heuristic
   int cfg_ks = 0;                                             // swapped kernel: k-blocks per stage (0 = 1)
   int cfg_tail = 1;                                           // normal kernel: pack left-over rows across images
+  int cfg_xr = -1, cfg_xslots = 0;                            // swapped kernel: tap-reuse variant (-1 = default), pixel ring depth
 };
 
 struct vgh_detector {
@@ -173,6 +174,23 @@ static void pick_tile_swap(int Ho, int Wo, int& tw, int& th, int max_px = 256) {
   }
 }
 
+// tap-reuse variant of the swapped kernel (3x3 stride 1): tile width a multiple of 8 pixels so that a row
+// of the tile is a whole number of 8-row swizzle atoms; the tile may overhang the map (TMA zero-fills the
+// load and clips the store).  Fewest MMA columns wasted wins; ties go to the taller tile (smaller halo share).
+static void pick_tile_swap_xr(int Ho, int Wo, int& tw, int& th, int max_px = 256) {
+  double best = -1.0;
+  tw = 8; th = 2;
+  const int wo8 = (Wo + 7) / 8 * 8;
+  for (int h = 1; h <= Ho && h <= 32 && h * 8 <= max_px; ++h) {
+    int w = max_px / h / 8 * 8;
+    if (w > wo8) w = wo8;
+    if (w < 8 || (w * h) % 16) continue;
+    const int tx = (Wo + w - 1) / w, ty = (Ho + h - 1) / h;
+    const double eff = static_cast<double>(Ho) * Wo / (static_cast<double>(tx) * ty * max_px);
+    if (eff > best - 1e-9) { best = eff > best ? eff : best; tw = w; th = h; }
+  }
+}
+
 // swapped kernel: G equal output-channel groups of gw <= 128 channels; a group's TMA box must be a
 // multiple of 16 bytes and the weight matrix must have 128 rows from every group start
 static bool swap_groups(const vgh_op_desc& q, const vgh_buf_desc& ob, int& G, int& gw) {
@@ -187,6 +205,21 @@ static bool swap_eligible(const vgh_op_desc& q, const vgh_buf_desc& ob) {
   int G, gw;
   if (!swap_groups(q, ob, G, gw)) return false;
   return !(q.res_buf >= 0 && ob.fp32);
+}
+
+static bool xr_eligible(const vgh_op_desc& q, const vgh_buf_desc& ob) {
+  return q.ksize == 3 && q.stride == 1 && !q.up && swap_eligible(q, ob);
+}
+// default for eligible ops: VGGHEADS_B200_XR = 0 (never) | 1 (whenever the swapped kernel runs a 3x3 stride-1 layer)
+static int xr_default() {
+  const char* e = getenv("VGGHEADS_B200_XR");
+  return (e && e[0] == '0') ? 0 : 1;
+}
+// test aid: VGGHEADS_B200_SWAP=1 makes the un-tuned heuristic pick the swapped kernel for every eligible op
+// (by default only large maps with Cout <= 128 do), so that small parity cases exercise it everywhere
+static bool swap_forced() {
+  const char* e = getenv("VGGHEADS_B200_SWAP");
+  return e && e[0] == '1';
 }
 
 static int auto_block_n(int cout, int up, int up_cout) {
@@ -211,12 +244,16 @@ static int build_conv(vgh_detector* d, OpRt& o) {
   L.stride = q.stride;
   L.Ho = q.up ? ib.H : (ib.H + q.stride - 1) / q.stride;
   L.Wo = q.up ? ib.W : (ib.W + q.stride - 1) / q.stride;
-  L.swap = o.cfg_swap >= 0 ? o.cfg_swap : (swap_eligible(q, ob) && q.cout <= 128 && !ob.fp32 && L.Ho * L.Wo >= 1024 ? 1 : 0);
+  L.swap = o.cfg_swap >= 0 ? o.cfg_swap
+                           : (swap_eligible(q, ob) && (swap_forced() || (q.cout <= 128 && !ob.fp32 && L.Ho * L.Wo >= 1024)) ? 1 : 0);
   if (L.swap) swap_groups(q, ob, L.ngroups, L.gw);
   if (L.swap && !swap_eligible(q, ob)) return fail(2, "op not eligible for the swapped kernel");
+  L.xr = (L.swap && xr_eligible(q, ob)) ? (o.cfg_xr >= 0 ? o.cfg_xr : xr_default()) : 0;
   if (o.cfg_tw > 0) { L.tw = o.cfg_tw; L.th = o.cfg_th; }
+  else if (L.xr) pick_tile_swap_xr(L.Ho, L.Wo, L.tw, L.th);
   else if (L.swap) pick_tile_swap(L.Ho, L.Wo, L.tw, L.th);
   else pick_tile(L.Ho, L.Wo, d->B, o.cfg_tail != 0, L.tw, L.th);
+  if (L.xr && L.tw % 8) return fail(2, "tap-reuse tiles must be a multiple of 8 pixels wide");
   L.tiles_x = (L.Wo + L.tw - 1) / L.tw;
   L.tiles_y = (L.Ho + L.th - 1) / L.th;
   // left-over rows: when the last row group of every image is mostly empty, pack those rows of
@@ -266,7 +303,21 @@ static int build_conv(vgh_detector* d, OpRt& o) {
     L.res_alpha = q.res_alpha;
   }
   L.mt = L.swap ? 1 : (o.cfg_mt > 0 ? o.cfg_mt : conv_default_mt(L.block_n));
-  if (L.swap) {
+  if (L.swap && L.xr) {
+    // two rings: pixel tiles with halo rows (xslots deep) and weight k-blocks (`stages` deep)
+    const int x_slot = (L.tw * (L.th + 2) * o.bk * 2 + 1023) & ~1023;
+    const int w_bytes = 128 * o.bk * 2;
+    const int staging = (L.tw * L.th * L.gw * (ob.fp32 ? 4 : 2) + 1023) & ~1023;
+    const int budget = 224 * 1024 - staging;
+    L.stg_bufs = 1;
+    L.ks = 1;
+    int xs = o.cfg_xslots > 0 ? o.cfg_xslots : 3;
+    while (xs > 2 && budget - xs * x_slot < 4 * w_bytes) --xs;
+    int ws = (budget - xs * x_slot) / w_bytes;
+    if (ws < 3) return fail(2, "tap-reuse variant does not fit shared memory (tile %dx%d, bk %d)", L.tw, L.th, o.bk);
+    L.xslots = xs;
+    L.stages = ws > 8 ? 8 : ws;
+  } else if (L.swap) {
     const int stage_bytes = 128 * o.bk * 2 + ((L.tw * L.th * o.bk * 2 + 1023) & ~1023);
     const int staging = (L.tw * L.th * L.gw * (ob.fp32 ? 4 : 2) + 1023) & ~1023;  // epilogue tile [pixels][channels]
     const int num_kb = L.ntaps * (q.cin / o.bk);
@@ -527,10 +578,32 @@ extern "C" int vgh_detector_autotune(vgh_detector* d, int iters, void* stream) {
     float best = 1e30f;
     int best_mt = 0, best_st = 0, best_swap = 0, best_tw = 0, best_th = 0, best_ks = 1;
     const int bn = o.L.block_n;
+    int best_xr = 0, best_xs = 0;
+    if (xr_eligible(o.d, d->bufs[o.d.out_buf]) && xr_default()) {
+      for (int max_px : {256, 192, 128}) {
+        for (int xs : {2, 3}) {
+          OpRt t = o;
+          t.cfg_ks = 1; t.cfg_swap = 1; t.cfg_mt = 0; t.cfg_stages = 0; t.cfg_xr = 1; t.cfg_xslots = xs;
+          pick_tile_swap_xr(o.L.Ho, o.L.Wo, t.cfg_tw, t.cfg_th, max_px);
+          if (build_conv(d, t) || t.L.xslots != xs || conv_launch(t.L, t.bk, s)) continue;
+          float ms = 1e30f;
+          for (int rep = 0; rep < 2; ++rep) {
+            cudaEventRecord(e0, s);
+            for (int i = 0; i < iters; ++i) conv_launch(t.L, t.bk, s);
+            cudaEventRecord(e1, s);
+            if (cudaStreamSynchronize(s) != cudaSuccess) return fail(7, "autotune (tap-reuse) launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            float m = 0.f;
+            cudaEventElapsedTime(&m, e0, e1);
+            if (m < ms) ms = m;
+          }
+          if (ms < best) { best = ms; best_swap = 1; best_mt = 1; best_st = 0; best_tw = t.cfg_tw; best_th = t.cfg_th; best_ks = 1; best_xr = 1; best_xs = xs; }
+        }
+      }
+    }
     if (swap_eligible(o.d, d->bufs[o.d.out_buf])) {
       for (int max_px : {256, 192, 128}) {  // pixel-tile size trades MMA width against pipeline depth
         OpRt t = o;
-        t.cfg_ks = 1;
+        t.cfg_ks = 1; t.cfg_xr = 0;
         if (max_px > 1000) {  // same tile sizes with several k-blocks per barrier round (shallow BK=32 blocks)
           max_px -= 1000;
           const int cblks = o.d.cin / o.bk;
@@ -551,7 +624,7 @@ extern "C" int vgh_detector_autotune(vgh_detector* d, int iters, void* stream) {
           cudaEventElapsedTime(&m, e0, e1);
           if (m < ms) ms = m;
         }
-        if (ms < best) { best = ms; best_swap = 1; best_mt = 1; best_st = 0; best_tw = t.cfg_tw; best_th = t.cfg_th; best_ks = t.cfg_ks; }
+        if (ms < best) { best = ms; best_swap = 1; best_mt = 1; best_st = 0; best_tw = t.cfg_tw; best_th = t.cfg_th; best_ks = t.cfg_ks; best_xr = 0; }
       }
     }
     for (int mt : {1, 2, 4}) {
@@ -578,7 +651,7 @@ extern "C" int vgh_detector_autotune(vgh_detector* d, int iters, void* stream) {
           cudaEventElapsedTime(&m, e0, e1);
           if (m < ms) ms = m;
         }
-        if (ms < best) { best = ms; best_mt = mt; best_st = st; best_swap = 0; }
+        if (ms < best) { best = ms; best_mt = mt; best_st = st; best_swap = 0; best_xr = 0; }
       }
     }
     if (best_mt) {
@@ -588,6 +661,8 @@ extern "C" int vgh_detector_autotune(vgh_detector* d, int iters, void* stream) {
       o.cfg_th = best_swap ? best_th : 0;
       o.cfg_mt = best_mt;
       o.cfg_stages = best_st;
+      o.cfg_xr = best_swap ? best_xr : 0;
+      o.cfg_xslots = best_xr ? best_xs : 0;
       int rc = build_conv(d, o);
       if (rc) return rc;
     }
@@ -600,7 +675,9 @@ extern "C" int vgh_detector_autotune(vgh_detector* d, int iters, void* stream) {
 extern "C" int vgh_detector_op_config(const vgh_detector* d, int op, int32_t* out6) {
   if (!d || op < 0 || op >= (int)d->ops.size() || !out6) return fail(1, "bad argument");
   const OpRt& o = d->ops[op];
-  out6[0] = o.L.swap ? -o.L.ks : o.L.mt; out6[1] = o.L.stages; out6[2] = o.L.block_n; out6[3] = o.bk; out6[4] = o.L.tw; out6[5] = o.L.th;
+  out6[0] = o.L.swap ? -o.L.ks : o.L.mt;
+  out6[1] = (o.L.swap && o.L.xr) ? 100 * o.L.xslots + o.L.stages : o.L.stages;  // tap reuse: 100*pixel slots + weight slots
+  out6[2] = o.L.block_n; out6[3] = o.bk; out6[4] = o.L.tw; out6[5] = o.L.th;
   return 0;
 }
 

@@ -296,3 +296,58 @@ def test_predict_batch_api():
         assert all(h.vertices_3d.shape == (5023, 3) for h in r.heads)
     with pytest.raises(ValueError):
         det.predict_batch([images[0]] * 4)
+
+
+@pytest.mark.parametrize("swap,xr", [("1", "1"), ("1", "0"), ("0", "0")])
+def test_kernel_variants_every_buffer_small(monkeypatch, swap, xr):
+    """The un-tuned heuristic only uses the operand-swapped kernel (and its 3x3 tap-reuse variant) on large
+    maps; force it onto every eligible layer of the small case - and switch the tap reuse off - so that each
+    variant is checked buffer by buffer against the CPU interpretation of the plan."""
+    from head_detector_b200.engine import Engine
+
+    monkeypatch.setenv("VGGHEADS_B200_SWAP", swap)
+    monkeypatch.setenv("VGGHEADS_B200_XR", xr)
+    S, B = 128, 3
+    eng = Engine(no.synthetic_weights(4), B, S)
+    used = [eng.op_config(i) for i, op in enumerate(eng.plan.ops) if op.kind == 1]
+    if swap == "1":
+        assert any(c["mt"] < 0 for c in used)
+        assert any(c["stages"] >= 100 for c in used) == (xr == "1")   # op_config reports tap reuse as 100*pixel slots + weight slots
+    torch.manual_seed(1)
+    img = torch.randint(0, 256, (B, S, S, 3), dtype=torch.uint8)
+    eng.forward(img.cuda())
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = pe.run_plan(eng.packed, img, emulate_bf16=True)
+    bad = []
+    for name, i in eng.plan.buf_names.items():
+        got, want = eng.read_buffer(name), ref[i]
+        scale = want.abs().max().item() + 1e-6
+        err = (got - want).abs()
+        if not (err.max().item() <= 2 ** -6 * scale + 1e-5 and err.mean().item() <= 2e-3 * scale):
+            bad.append((name, err.max().item(), err.mean().item(), scale))
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("xr", ["1", "0"])
+def test_kernel_variants_key_buffers_640(monkeypatch, xr):
+    """Reference resolution with the swapped kernel forced everywhere: 160/80/40/20-pixel maps, tiles that
+    overhang the 20- and 40-pixel maps, channel groups, residual tiles - with and without tap reuse."""
+    from head_detector_b200 import synth
+    from head_detector_b200.engine import Engine
+
+    monkeypatch.setenv("VGGHEADS_B200_SWAP", "1")
+    monkeypatch.setenv("VGGHEADS_B200_XR", xr)
+    B, S = 2, 640
+    eng = Engine(no.synthetic_weights(6), B, S)
+    img = synth.synthetic_images(B, S, seed=12)
+    eng.forward(img.cuda())
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = pe.run_plan(eng.packed, img, emulate_bf16=True)
+    for name in ("c2", "c3", "c4", "c5", "p3", "p4", "p5", "head1.flame_raw", "head2.flame_raw", "head3.reg_raw", "head1.reg_raw"):
+        got, want = eng.read_buffer(name), ref[eng.plan.buf_names[name]]
+        scale = want.abs().max().item() + 1e-6
+        err = (got - want).abs()
+        assert err.max().item() <= 2 ** -5 * scale + 1e-4, (name, err.max().item(), scale)
+        assert err.mean().item() <= 4e-3 * scale, (name, err.mean().item(), scale)
