@@ -425,7 +425,7 @@ int conv_make_tensor_maps(ConvLaunch& L, const void* in_base, int in_C, int in_H
   {
     cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)n_pad};
     cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
-    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)(L.swap ? 128 : L.block_n)};
+    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)(L.swap ? L.gw : L.block_n)};  // swapped: the group's own rows only
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&L.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

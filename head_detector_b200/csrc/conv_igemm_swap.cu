@@ -42,7 +42,10 @@ constexpr int kSwapThreads = 64 + 32 * kSwapEpiWarps;
 template <int BK, bool XR>
 __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const __grid_constant__ ConvLaunch p) {
   constexpr uint32_t kRowBytes = BK * 2;
-  constexpr uint32_t kWBytes = 128 * kRowBytes;  // weight tile: 128 cout rows
+  constexpr uint32_t kWBytes = 128 * kRowBytes;  // weight slot: 128 cout rows (the MMA M)
+  // only the group's own gw rows are fetched; the MMA still reads 128 rows, the rest is whatever the slot held -
+  // those accumulator lanes are never stored
+  const uint32_t w_tx = static_cast<uint32_t>(p.gw) * kRowBytes;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int npix = p.tw * p.th;                                   // UMMA N (multiple of 16, <= 256)
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
-      const uint32_t tx_bytes = kWBytes + x_bytes;
+      const uint32_t tx_bytes = w_tx + x_bytes;
       int stage = 0, xs = 0;
       uint32_t phase = 0, xphase = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
@@ -137,7 +140,7 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
               }
               for (int dy = 0; dy < 3; ++dy) {
                 mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-                mbar_arrive_expect_tx(full_bar + 8 * stage, kWBytes);
+                mbar_arrive_expect_tx(full_bar + 8 * stage, w_tx);
                 tma_load_2d(w_base + stage * kWBytes, &p.tmB, full_bar + 8 * stage, (dy * 3 + dx) * p.cin + cb * BK, n_base);
                 if (++stage == p.stages) {
                   stage = 0;

@@ -580,7 +580,15 @@ extern "C" int vgh_detector_autotune(vgh_detector* d, int iters, void* stream) {
     const int bn = o.L.block_n;
     int best_xr = 0, best_xs = 0;
     if (xr_eligible(o.d, d->bufs[o.d.out_buf]) && xr_default()) {
-      for (int max_px : {256, 192, 128}) {
+      int seen_tw[8], seen_th[8], n_seen = 0;
+      // tile sizes trade MMA width against wave quantisation (items / SMs) - measure them all
+      for (int max_px : {256, 224, 208, 192, 160, 128}) {
+        int ptw, pth;
+        pick_tile_swap_xr(o.L.Ho, o.L.Wo, ptw, pth, max_px);
+        bool dup = false;
+        for (int i = 0; i < n_seen; ++i) dup = dup || (seen_tw[i] == ptw && seen_th[i] == pth);
+        if (dup) continue;
+        seen_tw[n_seen] = ptw; seen_th[n_seen] = pth; ++n_seen;
         for (int xs : {2, 3}) {
           OpRt t = o;
           t.cfg_ks = 1; t.cfg_swap = 1; t.cfg_mt = 0; t.cfg_stages = 0; t.cfg_xr = 1; t.cfg_xslots = xs;

@@ -351,3 +351,36 @@ def test_kernel_variants_key_buffers_640(monkeypatch, xr):
         err = (got - want).abs()
         assert err.max().item() <= 2 ** -5 * scale + 1e-4, (name, err.max().item(), scale)
         assert err.mean().item() <= 4e-3 * scale, (name, err.mean().item(), scale)
+
+
+def test_autotuned_configuration_keeps_parity():
+    """bench.py runs the per-layer configurations `vgh_detector_autotune` picks (operand-swapped / tap-reuse /
+    multi-tile variants, tile shapes, pipeline depths).  Whatever it picks must compute the same network:
+    key buffers of an autotuned engine against the CPU interpretation, and the tuned engine against itself
+    before tuning (different kernels, same math: bf16-rounding-level agreement)."""
+    from head_detector_b200 import synth
+    from head_detector_b200.engine import Engine
+
+    B, S = 4, 640
+    eng = Engine(no.synthetic_weights(7), B, S)
+    img = synth.synthetic_images(B, S, seed=13)
+    eng.forward(img.cuda())
+    torch.cuda.synchronize()
+    names = ("c2", "c3", "c4", "c5", "p3", "p4", "p5", "head1.flame_raw", "head2.flame_raw", "head3.flame_raw", "head1.reg_raw", "head3.reg_raw")
+    before = {n: eng.read_buffer(n) for n in names}
+    cfg0 = [eng.op_config(i) for i, op in enumerate(eng.plan.ops) if op.kind == 1]
+    eng.autotune(2)
+    cfg1 = [eng.op_config(i) for i, op in enumerate(eng.plan.ops) if op.kind == 1]
+    assert cfg0 != cfg1, "autotune changed nothing - the test would not exercise the tuned kernels"
+    eng.forward(img.cuda())
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = pe.run_plan(eng.packed, img, emulate_bf16=True)
+    for name in names:
+        got, want = eng.read_buffer(name), ref[eng.plan.buf_names[name]]
+        scale = want.abs().max().item() + 1e-6
+        err = (got - want).abs()
+        assert err.max().item() <= 2 ** -5 * scale + 1e-4, (name, err.max().item(), scale)
+        assert err.mean().item() <= 4e-3 * scale, (name, err.mean().item(), scale)
+        drift = (got - before[name]).abs()
+        assert drift.max().item() <= 2 ** -5 * scale + 1e-4 and drift.mean().item() <= 4e-3 * scale, (name, drift.max().item())
