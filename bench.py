@@ -48,7 +48,7 @@ def ncu_conv_traffic():
     launches) from the committed ncu launch list of the same workload; None if the file is absent."""
     import csv
 
-    path = os.path.join(ROOT, "profiles", "r1_final_ncu_launches_metrics.csv")
+    path = os.path.join(ROOT, "profiles", "r1_xr_ncu_launches_metrics.csv")
     if not os.path.exists(path):
         return None
     tot = 0.0
@@ -350,7 +350,7 @@ def run_ours(args, rank, world, local_rank):
         ach = conv_flops / (conv_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "conv_igemm_swap_kernel / conv_igemm_kernel (125 launches/step)", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s",
                 "frac": ach / pk["tflops"], "peak_source": pk["src"], "traffic": ncu_conv_traffic(),
-                "traffic_note": "DRAM bytes of all conv_igemm launches of one step (profiles/r1_final_ncu_launches_metrics.csv); algorithmic activation bytes are ~13 GB/step",
+                "traffic_note": "DRAM bytes of all conv_igemm launches of one step (profiles/r1_xr_ncu_launches_metrics.csv); algorithmic activation bytes are ~13 GB/step",
                 "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_ms / all_ms,
                 "algorithmic_flops_per_step": conv_flops}
         if world == 1:
