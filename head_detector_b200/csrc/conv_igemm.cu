@@ -369,10 +369,12 @@ size_t conv_smem_bytes(const ConvLaunch& L, int bk) {
 
 // fills the derived scheduling fields (call after tiles / block_n / mt are set)
 void conv_finalize(ConvLaunch& L) {
-  if (L.swap) {  // one item = one (tw x th)-pixel tile; all (<=128) output channels
+  if (L.swap) {  // one item = one (tw x th)-pixel tile x one channel group; clusters take n_cl tiles of a group at a time
     L.mt = 1;
     L.n_tiles = 1;
-    L.num_items = L.tiles_x * L.tiles_y * L.B * L.ngroups;
+    if (L.cluster < 1) L.cluster = 1;
+    const int tiles = L.tiles_x * L.tiles_y * L.B;
+    L.num_items = ((tiles + L.cluster - 1) / L.cluster) * L.ngroups * L.cluster;
     const int npix = L.tw * L.th;
     L.acc_stages = (2 * npix <= 512) ? 2 : 1;
     int cols = 32;
@@ -425,7 +427,8 @@ int conv_make_tensor_maps(ConvLaunch& L, const void* in_base, int in_C, int in_H
   {
     cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)n_pad};
     cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
-    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)(L.swap ? L.gw : L.block_n)};  // swapped: the group's own rows only
+    // swapped: the group's own rows only (cluster pairs: each CTA fetches half of them)
+    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)(L.swap ? (L.cluster > 1 ? L.gw / L.cluster : L.gw) : L.block_n)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&L.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

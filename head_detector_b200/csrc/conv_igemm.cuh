@@ -45,6 +45,7 @@ struct ConvLaunch {
   int stg_bufs;                  // swapped kernel: epilogue staging tiles (2 = store of item i overlaps item i+1)
   int xr, xslots;                // swapped kernel, 3x3 stride 1: pixel tile + halo rows fetched once per column shift
                                  // and reused by the three row taps (xslots = pixel-tile ring depth; `stages` = weight ring)
+  int cluster;                   // swapped kernel: 1, or 2 = CTA pairs share every weight k-block (each fetches half, TMA multicast)
   int acc_stages, n_tiles, num_items;  // TMEM accumulator stages (1|2), N tiles, work items (persistent CTAs)
 };
 

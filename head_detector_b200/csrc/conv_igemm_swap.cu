@@ -27,6 +27,16 @@
 // traffic.  Weights (identical for every CTA, coalesced in L2) keep streaming tap by tap through their
 // own, deeper ring; the pixel ring has 2-3 slots.  K order: (cin block, dx, dy).
 //
+// Cluster variant (`p.cluster == 2`): the weight k-blocks are the same for every CTA but are not
+// coalesced in L2 - after the tap reuse they are more than half of the L2->SM bytes of a layer, and L2
+// bandwidth (8-9 TB/s of lts__t_bytes on every conv launch, profiles/r1_xr_ncu_launches_metrics.csv) is
+// what bounds the layers.  Two CTAs of a cluster work on two pixel tiles of the SAME channel group in
+// lock step; each fetches one half of every weight k-block and TMA-multicasts it into both CTAs' rings,
+// so the pair reads every weight byte from L2 once.  A slot is released to both producers by a multicast
+// tcgen05.commit from each consumer (empty barriers count 2).  Pixel tiles, TMEM, epilogue stay per CTA.
+// Measured neutral (the bound is per-SM ingest, which a multicast does not reduce) - off by default, kept as
+// the cluster plumbing (work-item mapping, cluster barriers, multicast commits) for cta_group::2 pairs.
+//
 // Everything else matches conv_igemm.cu: persistent CTAs, TMA (4-D pixel box with OOB zero fill =
 // padding, traversal stride = conv stride; 2-D weight box), mbarrier ring, double-buffered TMEM.
 #include <cstdio>
@@ -75,13 +85,30 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
+  // Work items: a cluster (1 or 2 CTAs) walks (tile group of n_cl pixel tiles, channel group); CTA r of the
+  // cluster takes tile r of the group.  With n_cl == 1 this is item = tile * ngroups + group as before.
+  const int n_cl = p.cluster;
+  const uint32_t cta_rank = n_cl > 1 ? cluster_ctarank() : 0u;
+  const int cl_id = blockIdx.x / n_cl, n_cls = gridDim.x / n_cl;
+  const int total_tiles = tiles_per_img * p.B;
+  const int n_citems = ((total_tiles + n_cl - 1) / n_cl) * p.ngroups;
+  // -> tile (clamped; `valid` false for the filler tile of an odd tile count: computed, never stored), group base
+  auto item_tile = [&](int ci, int& tile, int& n_base) -> bool {
+    const int tg = ci / p.ngroups;
+    n_base = (ci - tg * p.ngroups) * p.gw;
+    tile = tg * n_cl + static_cast<int>(cta_rank);
+    const bool valid = tile < total_tiles;
+    if (!valid) tile = total_tiles - 1;
+    return valid;
+  };
+  const uint16_t mc_mask = static_cast<uint16_t>((1u << n_cl) - 1u);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar + 8 * s, 1);
-      mbar_init(empty_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, n_cl);  // cluster: a weight slot is free once BOTH consumers have released it
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar + 8 * a, 1);
@@ -104,6 +131,7 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (n_cl > 1) cluster_sync_all();  // the peer's barriers exist before anything is multicast to / arrives on them
   uint32_t tmem_acc;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_acc) : "r"(tmem_slot));
   // everything above overlapped the previous kernel's tail (PDL); its outputs are needed from here on
@@ -113,6 +141,14 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
   const int cblks = p.cin / BK;
   const int num_kb = p.ntaps * cblks;
   const uint32_t acc_cols = static_cast<uint32_t>(npix);
+  // weight k-block fetch: the whole group (n_cl == 1) or this CTA's half of it, multicast to the pair
+  const uint32_t w_half = (static_cast<uint32_t>(p.gw) / 2u) * kRowBytes;
+  auto load_w = [&](uint32_t slot_addr, uint32_t bar, int k0, int n_base) {
+    if (n_cl > 1)
+      tma_load_2d_mc(slot_addr + cta_rank * w_half, &p.tmB, bar, k0, n_base + static_cast<int>(cta_rank) * (p.gw / 2), mc_mask);
+    else
+      tma_load_2d(slot_addr, &p.tmB, bar, k0, n_base);
+  };
 
   if (warp == 0) {
     if (lane == 0) {
@@ -120,9 +156,9 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
       const uint32_t tx_bytes = w_tx + x_bytes;
       int stage = 0, xs = 0;
       uint32_t phase = 0, xphase = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-        const int tile = item / p.ngroups;
-        const int n_base = (item - tile * p.ngroups) * gw;
+      for (int item = cl_id; item < n_citems; item += n_cls) {
+        int tile, n_base;
+        item_tile(item, tile, n_base);
         const int b_img = tile / tiles_per_img;
         const int t_in = tile - b_img * tiles_per_img;
         const int tyi = t_in / p.tiles_x;
@@ -141,7 +177,7 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
               for (int dy = 0; dy < 3; ++dy) {
                 mbar_wait(empty_bar + 8 * stage, phase ^ 1);
                 mbar_arrive_expect_tx(full_bar + 8 * stage, w_tx);
-                tma_load_2d(w_base + stage * kWBytes, &p.tmB, full_bar + 8 * stage, (dy * 3 + dx) * p.cin + cb * BK, n_base);
+                load_w(w_base + stage * kWBytes, full_bar + 8 * stage, (dy * 3 + dx) * p.cin + cb * BK, n_base);
                 if (++stage == p.stages) {
                   stage = 0;
                   phase ^= 1;
@@ -161,7 +197,7 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
             const int tx = tap - ty * p.kw;
             tma_load_4d(x_base + (stage * ks + q) * x_slot, &p.tmA, fb, p.cin_off + cb * BK, w0 * p.stride + tx - p.pad,
                         h0 * p.stride + ty - p.pad, b_img);
-            tma_load_2d(w_base + (stage * ks + q) * kWBytes, &p.tmB, fb, tap * p.cin + cb * BK, n_base);
+            load_w(w_base + (stage * ks + q) * kWBytes, fb, tap * p.cin + cb * BK, n_base);
             if (++cb == cblks) {
               cb = 0;
               ++tap;
@@ -182,7 +218,7 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
       uint32_t phase = 0, xphase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      for (int item = cl_id; item < n_citems; item += n_cls) {
         mbar_wait(tmem_empty_bar + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d = tmem_acc + acc * acc_cols;
@@ -202,7 +238,7 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
                 umma_bf16(d, w_desc + 2 * k, x_desc + 2 * k, idesc, accumulate);
                 accumulate = 1u;
               }
-              umma_commit(empty_bar + 8 * stage);
+              if (n_cl > 1) umma_commit_mc(empty_bar + 8 * stage, mc_mask); else umma_commit(empty_bar + 8 * stage);
               if (++stage == p.stages) {
                 stage = 0;
                 phase ^= 1;
@@ -231,7 +267,7 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
             for (int k = 0; k < BK / 16; ++k)
               umma_bf16(d, w_desc + 2 * k, x_desc + 2 * k, idesc, (kb | q | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar + 8 * stage);
+          if (n_cl > 1) umma_commit_mc(empty_bar + 8 * stage, mc_mask); else umma_commit(empty_bar + 8 * stage);
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
@@ -255,28 +291,30 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
     const bool has_res = p.res != nullptr;
     const bool leader = (ew == 0 && lane == 0);
     uint8_t* stile0 = smem_raw + (stage_base - smem_u32(smem_raw));
-    auto item_coords = [&](int item, int& b_img, int& h0, int& w0) {
-      const int tile = item / p.ngroups;
+    // cluster work item -> tile origin, channel-group base; false for a filler tile (computed, not stored)
+    auto item_coords = [&](int item, int& b_img, int& h0, int& w0, int& n_base) -> bool {
+      int tile;
+      const bool valid = item_tile(item, tile, n_base);
       b_img = tile / tiles_per_img;
       const int t_in = tile - b_img * tiles_per_img;
       const int tyi = t_in / p.tiles_x;
       h0 = tyi * p.th;
       w0 = (t_in - tyi * p.tiles_x) * p.tw;
+      return valid;
     };
-    if (has_res && leader && blockIdx.x < p.num_items) {  // residual tile of the first item -> buffer 0
-      int b_img, h0, w0;
-      item_coords(blockIdx.x, b_img, h0, w0);
+    if (has_res && leader && cl_id < n_citems) {  // residual tile of the first item -> buffer 0
+      int b_img, h0, w0, nb0;
+      item_coords(cl_id, b_img, h0, w0, nb0);
       tma_prefetch_desc(&p.tmRes);
       mbar_arrive_expect_tx(res_full_bar, stage_bytes);
-      tma_load_4d(stage_base, &p.tmRes, res_full_bar, p.res_coff + (blockIdx.x % p.ngroups) * gw, w0, h0, b_img);
+      tma_load_4d(stage_base, &p.tmRes, res_full_bar, p.res_coff + nb0, w0, h0, b_img);
     }
     if (leader) tma_prefetch_desc(&p.tmOut);
     int acc = 0, sb = 0;
     uint32_t acc_phase = 0, res_phase[2] = {0, 0};
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-      int b_img, h0, w0;
-      item_coords(item, b_img, h0, w0);
-      const int n_base = (item % p.ngroups) * gw;
+    for (int item = cl_id; item < n_citems; item += n_cls) {
+      int b_img, h0, w0, n_base;
+      const bool valid = item_coords(item, b_img, h0, w0, n_base);
       const float bias = ch_ok ? __ldg(p.bias + n_base + ch) : 0.f;
       mbar_wait(tmem_full_bar + 8 * acc, acc_phase);
       tc_fence_after();
@@ -320,16 +358,16 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
       named_bar_sync(1, 32 * kSwapEpiWarps);
       const int nsb = stg_bufs == 2 ? (sb ^ 1) : sb;
       if (leader) {
-        tma_store_4d(&p.tmOut, stage_base + sb * stage_slot, p.out_coff + n_base, w0, h0, b_img);
+        if (valid) tma_store_4d(&p.tmOut, stage_base + sb * stage_slot, p.out_coff + n_base, w0, h0, b_img);
         tma_store_commit();
         // the tile the NEXT item writes must have been read out by its previous store
         if (stg_bufs == 2) tma_store_wait_read_keep1(); else tma_store_wait_read();
-        const int next = item + gridDim.x;
-        if (has_res && next < p.num_items) {
-          int nb, nh, nw;
-          item_coords(next, nb, nh, nw);
+        const int next = item + n_cls;
+        if (has_res && next < n_citems) {
+          int nb, nh, nw, nn;
+          item_coords(next, nb, nh, nw, nn);
           mbar_arrive_expect_tx(res_full_bar + 8 * nsb, stage_bytes);
-          tma_load_4d(stage_base + nsb * stage_slot, &p.tmRes, res_full_bar + 8 * nsb, p.res_coff + (next % p.ngroups) * gw, nw, nh, nb);
+          tma_load_4d(stage_base + nsb * stage_slot, &p.tmRes, res_full_bar + 8 * nsb, p.res_coff + nn, nw, nh, nb);
         }
       }
       named_bar_sync(1, 32 * kSwapEpiWarps);
@@ -348,6 +386,8 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
     tc_fence_after();
     tmem_dealloc_dyn(tmem_acc, static_cast<uint32_t>(p.tmem_cols));
   }
+  // the peer's last slot releases land on this CTA's barriers: shared memory must outlive them
+  if (n_cl > 1) cluster_sync_all();
 }
 
 size_t conv_swap_smem_bytes(const ConvLaunch& L, int bk) {
@@ -373,15 +413,29 @@ static int launch_swap_t(const ConvLaunch& L, int sms, cudaStream_t stream, char
     configured = smem;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(L.num_items < sms ? L.num_items : sms);
+  const int n_cl = L.cluster > 1 ? L.cluster : 1;
+  int grid = L.num_items < sms ? L.num_items : sms;  // num_items counts CTA-level items (cluster items x cluster size)
+  grid -= grid % n_cl;
+  cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kSwapThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (n_cl > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = n_cl;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (conv_pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = conv_pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = na;
   cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm_swap_kernel<BK, XR>, L);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -392,6 +446,10 @@ static int launch_swap_t(const ConvLaunch& L, int sms, cudaStream_t stream, char
 }
 
 int conv_swap_launch(const ConvLaunch& L, int bk, int sms, cudaStream_t stream, char* err, size_t errlen) {
+  if (L.cluster != 1 && (L.cluster != 2 || L.gw % 16 || sms < 2)) {
+    snprintf(err, errlen, "swap conv: bad cluster configuration (cluster %d, group width %d)", L.cluster, L.gw);
+    return 7;
+  }
   if (L.xr) {
     if (L.ntaps != 9 || L.stride != 1 || L.tw % 8 || L.xslots < 2 || L.xslots > 8 || L.stages < 2) {
       snprintf(err, errlen, "swap conv: launch not eligible for the tap-reuse variant (taps %d stride %d tile %dx%d xslots %d stages %d)",

@@ -96,6 +96,7 @@ struct OpRt {
   int cfg_ks = 0;                                             // swapped kernel: k-blocks per stage (0 = 1)
   int cfg_tail = 1;                                           // normal kernel: pack left-over rows across images
   int cfg_xr = -1, cfg_xslots = 0;                            // swapped kernel: tap-reuse variant (-1 = default), pixel ring depth
+  int cfg_cluster = -1;                                       // swapped kernel: CTA pairs sharing the weight stream (-1 = default)
 };
 
 struct vgh_detector {
@@ -215,6 +216,14 @@ static int xr_default() {
   const char* e = getenv("VGGHEADS_B200_XR");
   return (e && e[0] == '0') ? 0 : 1;
 }
+// CTA-pair weight multicast: VGGHEADS_B200_CLUSTER = 1 turns it on for every eligible swapped launch (and makes it an
+// autotune candidate).  Off by default: measured neutral (same layer times to 0.5 %, profiles/r1_xr_cluster_ab.txt) -
+// what bounds these layers is the bytes each SM has to ingest, not the reads at the L2 slices, and a multicast
+// still delivers every byte to every SM.  Kept (and parity-tested) as the cluster plumbing cta_group::2 pairs need.
+static int cluster_default() {
+  const char* e = getenv("VGGHEADS_B200_CLUSTER");
+  return (e && e[0] == '1') ? 1 : 0;
+}
 // test aid: VGGHEADS_B200_SWAP=1 makes the un-tuned heuristic pick the swapped kernel for every eligible op
 // (by default only large maps with Cout <= 128 do), so that small parity cases exercise it everywhere
 static bool swap_forced() {
@@ -244,11 +253,16 @@ static int build_conv(vgh_detector* d, OpRt& o) {
   L.stride = q.stride;
   L.Ho = q.up ? ib.H : (ib.H + q.stride - 1) / q.stride;
   L.Wo = q.up ? ib.W : (ib.W + q.stride - 1) / q.stride;
+  // un-tuned default: the swapped kernel for Cout <= 128 on large maps and - with the tap reuse, which measured
+  // faster than every other variant on every 3x3 stride-1 layer of the network - for all of those
   L.swap = o.cfg_swap >= 0 ? o.cfg_swap
-                           : (swap_eligible(q, ob) && (swap_forced() || (q.cout <= 128 && !ob.fp32 && L.Ho * L.Wo >= 1024)) ? 1 : 0);
+                           : (swap_eligible(q, ob) && (swap_forced() || (xr_eligible(q, ob) && xr_default()) ||
+                                                       (q.cout <= 128 && !ob.fp32 && L.Ho * L.Wo >= 1024)) ? 1 : 0);
   if (L.swap) swap_groups(q, ob, L.ngroups, L.gw);
   if (L.swap && !swap_eligible(q, ob)) return fail(2, "op not eligible for the swapped kernel");
   L.xr = (L.swap && xr_eligible(q, ob)) ? (o.cfg_xr >= 0 ? o.cfg_xr : xr_default()) : 0;
+  // pairs need a group width whose halves are whole 8-row swizzle atoms
+  L.cluster = (L.swap && L.gw % 16 == 0 && (o.cfg_cluster >= 0 ? o.cfg_cluster : cluster_default())) ? 2 : 1;
   if (o.cfg_tw > 0) { L.tw = o.cfg_tw; L.th = o.cfg_th; }
   else if (L.xr) pick_tile_swap_xr(L.Ho, L.Wo, L.tw, L.th);
   else if (L.swap) pick_tile_swap(L.Ho, L.Wo, L.tw, L.th);
@@ -578,7 +592,7 @@ extern "C" int vgh_detector_autotune(vgh_detector* d, int iters, void* stream) {
     float best = 1e30f;
     int best_mt = 0, best_st = 0, best_swap = 0, best_tw = 0, best_th = 0, best_ks = 1;
     const int bn = o.L.block_n;
-    int best_xr = 0, best_xs = 0;
+    int best_xr = 0, best_xs = 0, best_cl = 0;
     if (xr_eligible(o.d, d->bufs[o.d.out_buf]) && xr_default()) {
       int seen_tw[8], seen_th[8], n_seen = 0;
       // tile sizes trade MMA width against wave quantisation (items / SMs) - measure them all
@@ -589,11 +603,11 @@ extern "C" int vgh_detector_autotune(vgh_detector* d, int iters, void* stream) {
         for (int i = 0; i < n_seen; ++i) dup = dup || (seen_tw[i] == ptw && seen_th[i] == pth);
         if (dup) continue;
         seen_tw[n_seen] = ptw; seen_th[n_seen] = pth; ++n_seen;
-        for (int xs : {2, 3}) {
+        for (int xs : {2, 3}) for (int cl = 0; cl <= cluster_default(); ++cl) {
           OpRt t = o;
-          t.cfg_ks = 1; t.cfg_swap = 1; t.cfg_mt = 0; t.cfg_stages = 0; t.cfg_xr = 1; t.cfg_xslots = xs;
+          t.cfg_ks = 1; t.cfg_swap = 1; t.cfg_mt = 0; t.cfg_stages = 0; t.cfg_xr = 1; t.cfg_xslots = xs; t.cfg_cluster = cl;
           pick_tile_swap_xr(o.L.Ho, o.L.Wo, t.cfg_tw, t.cfg_th, max_px);
-          if (build_conv(d, t) || t.L.xslots != xs || conv_launch(t.L, t.bk, s)) continue;
+          if (build_conv(d, t) || t.L.xslots != xs || t.L.cluster != cl + 1 || conv_launch(t.L, t.bk, s)) continue;
           float ms = 1e30f;
           for (int rep = 0; rep < 2; ++rep) {
             cudaEventRecord(e0, s);
@@ -604,14 +618,14 @@ extern "C" int vgh_detector_autotune(vgh_detector* d, int iters, void* stream) {
             cudaEventElapsedTime(&m, e0, e1);
             if (m < ms) ms = m;
           }
-          if (ms < best) { best = ms; best_swap = 1; best_mt = 1; best_st = 0; best_tw = t.cfg_tw; best_th = t.cfg_th; best_ks = 1; best_xr = 1; best_xs = xs; }
+          if (ms < best) { best = ms; best_swap = 1; best_mt = 1; best_st = 0; best_tw = t.cfg_tw; best_th = t.cfg_th; best_ks = 1; best_xr = 1; best_xs = xs; best_cl = cl; }
         }
       }
     }
     if (swap_eligible(o.d, d->bufs[o.d.out_buf])) {
-      for (int max_px : {256, 192, 128}) {  // pixel-tile size trades MMA width against pipeline depth
+      for (int max_px : {256, 192, 128}) for (int cl = 0; cl <= cluster_default(); ++cl) {  // pixel-tile size trades MMA width against pipeline depth
         OpRt t = o;
-        t.cfg_ks = 1; t.cfg_xr = 0;
+        t.cfg_ks = 1; t.cfg_xr = 0; t.cfg_cluster = cl;
         if (max_px > 1000) {  // same tile sizes with several k-blocks per barrier round (shallow BK=32 blocks)
           max_px -= 1000;
           const int cblks = o.d.cin / o.bk;
@@ -621,7 +635,7 @@ extern "C" int vgh_detector_autotune(vgh_detector* d, int iters, void* stream) {
         t.cfg_swap = 1; t.cfg_mt = 0; t.cfg_stages = 0;
         pick_tile_swap(o.L.Ho, o.L.Wo, t.cfg_tw, t.cfg_th, max_px);
         if (max_px != 256 && t.cfg_tw * t.cfg_th > max_px) continue;
-        if (build_conv(d, t) || conv_launch(t.L, t.bk, s)) continue;
+        if (build_conv(d, t) || t.L.cluster != cl + 1 || conv_launch(t.L, t.bk, s)) continue;
         float ms = 1e30f;
         for (int rep = 0; rep < 2; ++rep) {  // best of two timed bursts: the clock / power state is noisy
           cudaEventRecord(e0, s);
@@ -632,7 +646,7 @@ extern "C" int vgh_detector_autotune(vgh_detector* d, int iters, void* stream) {
           cudaEventElapsedTime(&m, e0, e1);
           if (m < ms) ms = m;
         }
-        if (ms < best) { best = ms; best_swap = 1; best_mt = 1; best_st = 0; best_tw = t.cfg_tw; best_th = t.cfg_th; best_ks = t.cfg_ks; best_xr = 0; }
+        if (ms < best) { best = ms; best_swap = 1; best_mt = 1; best_st = 0; best_tw = t.cfg_tw; best_th = t.cfg_th; best_ks = t.cfg_ks; best_xr = 0; best_cl = cl; }
       }
     }
     for (int mt : {1, 2, 4}) {
@@ -670,6 +684,7 @@ extern "C" int vgh_detector_autotune(vgh_detector* d, int iters, void* stream) {
       o.cfg_mt = best_mt;
       o.cfg_stages = best_st;
       o.cfg_xr = best_swap ? best_xr : 0;
+      o.cfg_cluster = best_swap ? best_cl : 0;
       o.cfg_xslots = best_xr ? best_xs : 0;
       int rc = build_conv(d, o);
       if (rc) return rc;
@@ -683,7 +698,7 @@ extern "C" int vgh_detector_autotune(vgh_detector* d, int iters, void* stream) {
 extern "C" int vgh_detector_op_config(const vgh_detector* d, int op, int32_t* out6) {
   if (!d || op < 0 || op >= (int)d->ops.size() || !out6) return fail(1, "bad argument");
   const OpRt& o = d->ops[op];
-  out6[0] = o.L.swap ? -o.L.ks : o.L.mt;
+  out6[0] = o.L.swap ? -(o.L.ks + 10 * (o.L.cluster - 1)) : o.L.mt;  // swapped: -ks, -1x = CTA pairs (weight multicast)
   out6[1] = (o.L.swap && o.L.xr) ? 100 * o.L.xslots + o.L.stages : o.L.stages;  // tap reuse: 100*pixel slots + weight slots
   out6[2] = o.L.block_n; out6[3] = o.bk; out6[4] = o.L.tw; out6[5] = o.L.th;
   return 0;

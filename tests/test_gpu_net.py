@@ -298,8 +298,8 @@ def test_predict_batch_api():
         det.predict_batch([images[0]] * 4)
 
 
-@pytest.mark.parametrize("swap,xr", [("1", "1"), ("1", "0"), ("0", "0")])
-def test_kernel_variants_every_buffer_small(monkeypatch, swap, xr):
+@pytest.mark.parametrize("swap,xr,cluster", [("1", "1", "1"), ("1", "1", "0"), ("1", "0", "1"), ("1", "0", "0"), ("0", "0", "0")])
+def test_kernel_variants_every_buffer_small(monkeypatch, swap, xr, cluster):
     """The un-tuned heuristic only uses the operand-swapped kernel (and its 3x3 tap-reuse variant) on large
     maps; force it onto every eligible layer of the small case - and switch the tap reuse off - so that each
     variant is checked buffer by buffer against the CPU interpretation of the plan."""
@@ -307,12 +307,14 @@ def test_kernel_variants_every_buffer_small(monkeypatch, swap, xr):
 
     monkeypatch.setenv("VGGHEADS_B200_SWAP", swap)
     monkeypatch.setenv("VGGHEADS_B200_XR", xr)
+    monkeypatch.setenv("VGGHEADS_B200_CLUSTER", cluster)   # CTA pairs sharing the weight stream (odd tile counts: filler tiles)
     S, B = 128, 3
     eng = Engine(no.synthetic_weights(4), B, S)
     used = [eng.op_config(i) for i, op in enumerate(eng.plan.ops) if op.kind == 1]
     if swap == "1":
         assert any(c["mt"] < 0 for c in used)
         assert any(c["stages"] >= 100 for c in used) == (xr == "1")   # op_config reports tap reuse as 100*pixel slots + weight slots
+        assert any(c["mt"] <= -11 for c in used) == (cluster == "1")  # ... and CTA pairs as mt = -(10 + k-blocks per stage)
     torch.manual_seed(1)
     img = torch.randint(0, 256, (B, S, S, 3), dtype=torch.uint8)
     eng.forward(img.cuda())
@@ -329,8 +331,8 @@ def test_kernel_variants_every_buffer_small(monkeypatch, swap, xr):
     assert not bad, bad
 
 
-@pytest.mark.parametrize("xr", ["1", "0"])
-def test_kernel_variants_key_buffers_640(monkeypatch, xr):
+@pytest.mark.parametrize("xr,cluster", [("1", "1"), ("0", "1"), ("1", "0"), ("0", "0")])
+def test_kernel_variants_key_buffers_640(monkeypatch, xr, cluster):
     """Reference resolution with the swapped kernel forced everywhere: 160/80/40/20-pixel maps, tiles that
     overhang the 20- and 40-pixel maps, channel groups, residual tiles - with and without tap reuse."""
     from head_detector_b200 import synth
@@ -338,6 +340,7 @@ def test_kernel_variants_key_buffers_640(monkeypatch, xr):
 
     monkeypatch.setenv("VGGHEADS_B200_SWAP", "1")
     monkeypatch.setenv("VGGHEADS_B200_XR", xr)
+    monkeypatch.setenv("VGGHEADS_B200_CLUSTER", cluster)
     B, S = 2, 640
     eng = Engine(no.synthetic_weights(6), B, S)
     img = synth.synthetic_images(B, S, seed=12)
