@@ -594,19 +594,40 @@ extern "C" int vgh_detector_autotune(vgh_detector* d, int iters, void* stream) {
     const int bn = o.L.block_n;
     int best_xr = 0, best_xs = 0, best_cl = 0;
     if (xr_eligible(o.d, d->bufs[o.d.out_buf]) && xr_default()) {
-      int seen_tw[8], seen_th[8], n_seen = 0;
-      // tile sizes trade MMA width against wave quantisation (items / SMs) - measure them all
-      for (int max_px : {256, 224, 208, 192, 160, 128}) {
-        int ptw, pth;
-        pick_tile_swap_xr(o.L.Ho, o.L.Wo, ptw, pth, max_px);
-        bool dup = false;
-        for (int i = 0; i < n_seen; ++i) dup = dup || (seen_tw[i] == ptw && seen_th[i] == pth);
-        if (dup) continue;
-        seen_tw[n_seen] = ptw; seen_th[n_seen] = pth; ++n_seen;
+      // candidate tiles: every admissible shape ranked by a coarse cost model - waves of work items over the SMs
+      // x (MMA columns + a share for the pixel rows each item ingests + a fixed per-item cost) - and the best six
+      // are MEASURED; the shape the un-tuned default would take is always among them
+      struct Cand { int tw, th; double est; };
+      Cand cands[8];
+      int n_cand = 0;
+      {
+        int sms = 148, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int Ho = o.L.Ho, Wo = o.L.Wo, wo8 = (Wo + 7) / 8 * 8;
+        int G = 1, gw = 0;
+        swap_groups(o.d, d->bufs[o.d.out_buf], G, gw);
+        int dtw, dth;
+        pick_tile_swap_xr(Ho, Wo, dtw, dth);
+        cands[n_cand++] = {dtw, dth, -1.0};
+        for (int th = 1; th <= Ho && th <= 32; ++th)
+          for (int tw = 8; tw <= wo8 && tw * th <= 256; tw += 8) {
+            if ((tw * th) % 16 || tw * th < 64 || (tw == dtw && th == dth)) continue;
+            const long items = static_cast<long>((Wo + tw - 1) / tw) * ((Ho + th - 1) / th) * d->B * G;
+            const double waves = static_cast<double>((items + sms - 1) / sms);
+            const double est = waves * (tw * th + 0.35 * 3.0 * tw * (th + 2) + 40.0);
+            if (n_cand < 7) cands[n_cand++] = {tw, th, est};  // slots 1..6: the cheapest so far, ascending
+            else if (est < cands[6].est) cands[6] = {tw, th, est};
+            else continue;
+            for (int i = n_cand - 1; i > 1 && cands[i].est < cands[i - 1].est; --i) { Cand c = cands[i]; cands[i] = cands[i - 1]; cands[i - 1] = c; }
+          }
+      }
+      for (int ci = 0; ci < n_cand; ++ci) {
+        const int ptw = cands[ci].tw, pth = cands[ci].th;
         for (int xs : {2, 3}) for (int cl = 0; cl <= cluster_default(); ++cl) {
           OpRt t = o;
           t.cfg_ks = 1; t.cfg_swap = 1; t.cfg_mt = 0; t.cfg_stages = 0; t.cfg_xr = 1; t.cfg_xslots = xs; t.cfg_cluster = cl;
-          pick_tile_swap_xr(o.L.Ho, o.L.Wo, t.cfg_tw, t.cfg_th, max_px);
+          t.cfg_tw = ptw; t.cfg_th = pth;
           if (build_conv(d, t) || t.L.xslots != xs || t.L.cluster != cl + 1 || conv_launch(t.L, t.bk, s)) continue;
           float ms = 1e30f;
           for (int rep = 0; rep < 2; ++rep) {
