@@ -20,7 +20,7 @@ from . import arch
 from .detection_result import PredictionResult
 from .engine import Engine
 from .flame import FLAMELayer
-from .head_info import Bbox, FlameParams, HeadMetadata
+from .head_info import FLAME_CONSTS, Bbox, FlameParams, HeadMetadata
 from .preprocess import letterbox_batch, letterbox_geometry
 from .utils import rpy_from_rotations
 
@@ -88,30 +88,54 @@ class HeadDetector:
                 "offsets": eng.head_offsets, "params": eng.head_params(n), "vertices": eng.head_verts(n),
                 "rotations": eng.head_rot(n)}
 
+    def _parse_batch(self, out: Dict[str, torch.Tensor], caches: List[Dict[str, Any]]) -> List[List[HeadMetadata]]:
+        """detector.py:61-90 for the first len(caches) images of a batch, vectorised over the batch: ONE
+        device->host copy per tensor, box un-letterboxing / rounding, roll-pitch-yaw and the `scale /= scale`
+        of detector.py:79 as whole-batch array ops, parameter fields as views of one [N,413] host tensor
+        (`Tensor.split`), so that the per-head Python work is only the construction of the result objects."""
+        S, n_img = self._image_size, len(caches)
+        offsets = out["offsets"].cpu().numpy().astype(np.int64)
+        total = int(offsets[n_img])
+        cnt = np.diff(offsets[:n_img + 1])
+        img_of = np.repeat(np.arange(n_img), cnt)                                   # image of every head
+        slot = np.arange(total) - np.repeat(offsets[:n_img], cnt)                   # its slot in the image's keep list
+        boxes = out["keep_boxes"][:n_img].cpu().numpy()[img_of, slot]               # [N,4]
+        scores = out["keep_scores"][:n_img].cpu().numpy()[img_of, slot]
+        verts = out["vertices"][:total].cpu().numpy()                               # un-padded / un-scaled on the device
+        params = out["params"][:total].cpu()
+        rots = out["rotations"][:total].cpu().numpy()
+        pad = np.array([[c["padding"][0], c["padding"][1]] for c in caches], dtype=np.float32).reshape(n_img, 2)[img_of]
+        scale64 = np.array([c["scale"] for c in caches], dtype=np.float64).reshape(n_img)[img_of]
+        scale = scale64.astype(np.float32)
+        boxes = boxes.clip(0, S)
+        boxes[:, [0, 2]] -= pad[:, :1]
+        boxes[:, [1, 3]] -= pad[:, 1:]
+        boxes /= scale[:, None]
+        boxes = np.rint(boxes).astype(int)
+        wh = boxes[:, 2:] - boxes[:, :2]
+        poses = rpy_from_rotations(rots)
+        fields, at = {}, 0
+        for key in ("shape", "expression", "jaw", "rotation", "eyeballs", "neck", "translation", "scale"):   # READ order, head_info.py:54-78
+            width = FLAME_CONSTS[key]
+            col = params[:, at:at + width]
+            if key == "scale":
+                col = col / torch.from_numpy(scale64).to(col.dtype)[:, None]        # detector.py:79
+            fields[key] = col.split(1) if total else ()
+            at += width
+        heads: List[List[HeadMetadata]] = [[] for _ in range(n_img)]
+        for i in range(total):
+            fp = FlameParams(**{k: v[i] for k, v in fields.items()})
+            b = boxes[i]
+            heads[img_of[i]].append(HeadMetadata(bbox=Bbox(x=b[0], y=b[1], w=wh[i, 0], h=wh[i, 1]), score=scores[i],
+                                                 flame_params=fp, vertices_3d=verts[i], head_pose=poses[i]))
+        return heads
+
     def _parse_predictions(self, out: Dict[str, torch.Tensor], img: int, cache: Dict[str, Any]) -> List[HeadMetadata]:
         """detector.py:61-90 for image `img` of the batch."""
-        pad, scale, S = cache["padding"], cache["scale"], self._image_size
         lo, hi = int(out["offsets"][img]), int(out["offsets"][img + 1])
-        n = hi - lo
-        boxes = out["keep_boxes"][img, :n].cpu().numpy()
-        scores = out["keep_scores"][img, :n].cpu().numpy()
-        verts = out["vertices"][lo:hi].cpu().numpy()          # already un-padded / un-scaled on the device
-        params = out["params"][lo:hi].cpu()
-        rots = out["rotations"][lo:hi].cpu().numpy()
-        boxes = boxes.clip(0, S)
-        boxes[:, [0, 2]] -= pad[0]
-        boxes[:, [1, 3]] -= pad[1]
-        boxes /= scale
-        boxes = np.rint(boxes).astype(int)
-        poses = rpy_from_rotations(rots)
-        heads = []
-        for i in range(n):
-            fp = FlameParams.from_3dmm(params[i:i + 1])
-            fp.scale = fp.scale / scale
-            b = boxes[i]
-            heads.append(HeadMetadata(bbox=Bbox(x=b[0], y=b[1], w=b[2] - b[0], h=b[3] - b[1]), score=scores[i],
-                                      flame_params=fp, vertices_3d=verts[i], head_pose=poses[i]))
-        return heads
+        one = {"offsets": torch.tensor([0, hi - lo]), "keep_boxes": out["keep_boxes"][img:img + 1], "keep_scores": out["keep_scores"][img:img + 1],
+               "vertices": out["vertices"][lo:hi], "params": out["params"][lo:hi], "rotations": out["rotations"][lo:hi]}
+        return self._parse_batch(one, [cache])[0]
 
     def predict_batch(self, images: List[Any], confidence_threshold: float = 0.5) -> List[PredictionResult]:
         """Batched `__call__` (extension; semantics of yolo_heads_post_prediction_callback.py:55-97: every image
@@ -122,9 +146,8 @@ class HeadDetector:
         originals = [self._convert_image(im) for im in images]
         batch, xf, caches = self._prepare_batch(originals)
         out = self.detect_batch(batch, confidence_threshold, xf)
-        out = {k: v.cpu() if k in ("offsets", "keep_cnt") else v for k, v in out.items()}
-        return [PredictionResult(original_image=o, heads=self._parse_predictions(out, i, c))
-                for i, (o, c) in enumerate(zip(originals, caches))]
+        heads = self._parse_batch(out, caches)
+        return [PredictionResult(original_image=o, heads=h) for o, h in zip(originals, heads)]
 
     def _prepare_batch(self, originals: List[np.ndarray]):
         """`_preprocess` (detector.py:54-56) for up to batch_size images: letterboxed uint8 cuda batch
