@@ -7,11 +7,15 @@
 // HBM-bound by design: algorithmic bytes = source image bytes read once + S*S*3 written.  One thread
 // per destination pixel evaluates the 8x8 taps of its three channels from L1/L2 (neighbouring threads
 // share 7/8 of their source columns); the per-column / per-row int16 weight tables are built on the
-// host (2*(new_w+new_h) sin/cos evaluations per image, double precision like OpenCV) and staged
-// through stream-ordered scratch memory.
+// host (sin/cos in double precision like OpenCV; cached per (source, destination) extent pair) and
+// staged through stream-ordered scratch memory.
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <utility>
 #include <vector>
 
 #include "letterbox.cuh"
@@ -43,11 +47,45 @@ __global__ void __launch_bounds__(kLbTileX* kLbTileY) letterbox_kernel(const uin
   o[2] = px[2];
 }
 
+// Axis tables are pure functions of (source extent, destination extent): built once per pair (video
+// frames and photo batches repeat a handful of sizes) and shared by every image / axis that uses the pair.
+struct AxisTable {
+  std::vector<int32_t> ofs;
+  std::vector<int16_t> coef;
+};
+static AxisTable axis_table(int src, int dst) {  // by value: copied under the lock, the cache may be reset by another thread
+  static std::mutex mu;
+  static std::map<std::pair<int, int>, AxisTable> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find({src, dst});
+  if (it == cache.end()) {
+    if (cache.size() > 256) cache.clear();  // bounded
+    AxisTable t;
+    t.ofs.resize(dst);
+    t.coef.resize(static_cast<size_t>(dst) * 8);
+    lanczos4_axis_tables(src, dst, t.ofs.data(), t.coef.data());
+    it = cache.emplace(std::make_pair(src, dst), std::move(t)).first;
+  }
+  return it->second;
+}
+
 int letterbox_launch(const uint8_t* src_dev, const int64_t* offsets, const int32_t* heights, const int32_t* widths, int n, int S,
                      uint8_t* out_dev, float* xform_host, cudaStream_t stream, char* err, size_t errlen) {
   if (n == 0) return 0;
   std::vector<LetterboxImage> imgs(n);
-  int entries = 0;
+  std::map<std::pair<int, int>, int> placed;  // (src, dst) -> first table entry of this call
+  std::vector<int32_t> ofs;
+  std::vector<int16_t> coef;
+  auto place = [&](int src, int dst) {
+    auto it = placed.find({src, dst});
+    if (it != placed.end()) return it->second;
+    const int at = static_cast<int>(ofs.size());
+    const AxisTable t = axis_table(src, dst);
+    ofs.insert(ofs.end(), t.ofs.begin(), t.ofs.end());
+    coef.insert(coef.end(), t.coef.begin(), t.coef.end());
+    placed[{src, dst}] = at;
+    return at;
+  };
   for (int i = 0; i < n; ++i) {
     LetterboxImage& g = imgs[i];
     if (!letterbox_geometry(heights[i], widths[i], S, &g)) {
@@ -55,9 +93,8 @@ int letterbox_launch(const uint8_t* src_dev, const int64_t* offsets, const int32
       return 1;
     }
     g.src_off = offsets[i];
-    g.xtab = entries;
-    g.ytab = entries + g.new_w;
-    entries += g.new_w + g.new_h;
+    g.xtab = place(g.w, g.new_w);
+    g.ytab = place(g.h, g.new_h);
     if (xform_host) {
       xform_host[i * 3 + 0] = static_cast<float>(g.pad_x);
       xform_host[i * 3 + 1] = static_cast<float>(g.pad_y);
@@ -65,23 +102,37 @@ int letterbox_launch(const uint8_t* src_dev, const int64_t* offsets, const int32
       xform_host[i * 3 + 2] = static_cast<float>(static_cast<double>(S) / longest);  // detector.py:46
     }
   }
-  std::vector<int32_t> ofs(entries);
-  std::vector<int16_t> coef(static_cast<size_t>(entries) * 8);
-  for (int i = 0; i < n; ++i) {
-    const LetterboxImage& g = imgs[i];
-    lanczos4_axis_tables(g.w, g.new_w, ofs.data() + g.xtab, coef.data() + static_cast<size_t>(g.xtab) * 8);
-    lanczos4_axis_tables(g.h, g.new_h, ofs.data() + g.ytab, coef.data() + static_cast<size_t>(g.ytab) * 8);
-  }
-  // one stream-ordered scratch block: [coef (16 B per entry) | ofs | image records]
+  // one stream-ordered device scratch block [coef (16 B per entry) | ofs | image records], filled by ONE copy
+  // from a per-thread pinned staging buffer (an event guards its reuse by the next call of this thread)
   const size_t coef_bytes = coef.size() * sizeof(int16_t);
   const size_t ofs_bytes = (ofs.size() * sizeof(int32_t) + 15) & ~static_cast<size_t>(15);
   const size_t img_bytes = imgs.size() * sizeof(LetterboxImage);
+  const size_t total_bytes = coef_bytes + ofs_bytes + img_bytes;
+  struct Staging {
+    uint8_t* host = nullptr;
+    size_t cap = 0;
+    cudaEvent_t done = nullptr;
+  };
+  static thread_local Staging st;
+  cudaError_t e = cudaSuccess;
+  if (st.done) e = cudaEventSynchronize(st.done);  // the previous call's copy has left the buffer
+  if (e == cudaSuccess && st.cap < total_bytes) {
+    if (st.host) cudaFreeHost(st.host);
+    st.host = nullptr;
+    st.cap = 0;
+    e = cudaMallocHost(reinterpret_cast<void**>(&st.host), total_bytes * 2);
+    if (e == cudaSuccess) st.cap = total_bytes * 2;
+  }
+  if (e == cudaSuccess && !st.done) e = cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming);
   uint8_t* scratch = nullptr;
-  cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&scratch), coef_bytes + ofs_bytes + img_bytes, stream);
-  // pageable sources: cudaMemcpyAsync returns once the data is staged, the vectors may go out of scope
-  if (e == cudaSuccess) e = cudaMemcpyAsync(scratch, coef.data(), coef_bytes, cudaMemcpyHostToDevice, stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(scratch + coef_bytes, ofs.data(), ofs.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(scratch + coef_bytes + ofs_bytes, imgs.data(), img_bytes, cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) {
+    memcpy(st.host, coef.data(), coef_bytes);
+    memcpy(st.host + coef_bytes, ofs.data(), ofs.size() * sizeof(int32_t));
+    memcpy(st.host + coef_bytes + ofs_bytes, imgs.data(), img_bytes);
+    e = cudaMallocAsync(reinterpret_cast<void**>(&scratch), total_bytes, stream);
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(scratch, st.host, total_bytes, cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) e = cudaEventRecord(st.done, stream);
   if (e == cudaSuccess) {
     const dim3 grid((S + kLbTileX - 1) / kLbTileX, (S + kLbTileY - 1) / kLbTileY, n);
     letterbox_kernel<<<grid, dim3(kLbTileX, kLbTileY), 0, stream>>>(

@@ -49,8 +49,8 @@ def letterbox_batch(images: Sequence[np.ndarray], image_size: int = 640, out: Op
         total += (im.size + 255) & ~255
     staging = torch.empty(total, dtype=torch.uint8, pin_memory=True)
     flat = staging.numpy()
-    for off, im in zip(offsets, imgs):
-        flat[off:off + im.size] = im.reshape(-1)
+    for off, im in zip(offsets, imgs):   # one memcpy per frame into pinned memory (a thread pool measured slower on the GPU box)
+        np.copyto(flat[off:off + im.size], im.reshape(-1))
     src = staging.cuda(non_blocking=True)
     heights = np.array([im.shape[0] for im in imgs], np.int32)
     widths = np.array([im.shape[1] for im in imgs], np.int32)
