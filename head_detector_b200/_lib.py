@@ -13,11 +13,11 @@ NUM_PARAMS = 413
 
 (OUT_BOXES, OUT_SCORES, OUT_KEEP_IDX, OUT_KEEP_CNT, OUT_KEEP_BOXES, OUT_KEEP_SCORES, OUT_HEAD_OFFSETS, OUT_HEAD_PARAMS,
  OUT_HEAD_VERTS, OUT_HEAD_ROT, OUT_INPUT) = range(11)
-OP_STEM, OP_CONV, OP_SPP = 0, 1, 2
+OP_STEM, OP_CONV, OP_SPP, OP_PATCH_GATHER, OP_PATCH_MASK = 0, 1, 2, 3, 4
 
 
 class BufDesc(C.Structure):
-    _fields_ = [("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("fp32", C.c_int32)]
+    _fields_ = [("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("fp32", C.c_int32), ("stack", C.c_int32)]
 
 
 class OpDesc(C.Structure):
@@ -30,7 +30,7 @@ class OpDesc(C.Structure):
         ("res_buf", C.c_int32), ("res_coff", C.c_int32), ("res_alpha", C.c_float),
         ("n_pad", C.c_int32), ("k_total", C.c_int32), ("block_n", C.c_int32),
         ("w_off", C.c_int64), ("b_off", C.c_int64),
-        ("lane", C.c_int32), ("reserved", C.c_int32),
+        ("lane", C.c_int32), ("level", C.c_int32),
     ]
 
 
@@ -41,7 +41,7 @@ class NetDesc(C.Structure):
         ("weights_host", C.c_void_p), ("n_weights", C.c_int64),
         ("bias_host", C.c_void_p), ("n_bias", C.c_int64),
         ("reg_buf", C.c_int32 * 3), ("flame_buf", C.c_int32 * 3),
-        ("keep_k", C.c_int32),
+        ("keep_k", C.c_int32), ("n_dense_ops", C.c_int32),
     ]
 
 

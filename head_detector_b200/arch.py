@@ -34,6 +34,10 @@ HEADS = [(96, 128, 8), (192, 256, 16), (384, 512, 32)]  # (in, bbox_inter, strid
 FLAME_INTER = 256
 TOWERS = [("shape", 256, 128), ("expr", 128, 64), ("rot", 32, 6), ("jaw", 32, 3), ("scale", 32, 1), ("transl", 32, 3)]
 REG_ROWS, FLAME_ROWS = 80, 208  # 68+1 (+pad) ; 128+64+6+3+3+1 (+pad)
+# Sparse heads: the FLAME branch of a head level (pose stem -> 3 tower layers -> output convs) is only ever read at the
+# anchors that survive NMS.  Its receptive field there is 7x7 pixels of the level's feature map, so the branch can run
+# on PATCH x PATCH windows gathered around the survivors (window origin = anchor - PATCH_C) instead of the whole map.
+PATCH, PATCH_C = 8, 3
 # raw flame row layout: [shape128 | expr64 | rot6 | jaw3 | transl3 | scale1 | pad3]
 RAW_ROW_OFF = {"shape": 0, "expr": 128, "rot": 192, "jaw": 198, "transl": 201, "scale": 204}
 
@@ -65,6 +69,7 @@ class Op:
     n_pad: int = 0
     label: str = ""
     lane: int = 0  # independent branches of the graph run on separate lanes (CUDA streams / graph branches)
+    level: int = 0  # survivor-patch ops (sparse heads): 1 + head level whose patch stack the op works on; 0 = dense op
 
 
 class Plan:
@@ -77,6 +82,10 @@ class Plan:
         self.reg_buf: List[int] = []
         self.flame_buf: List[int] = []
         self.lane = 0  # lane given to ops appended from now on
+        self.level = 0  # level tag given to ops appended from now on (sparse heads)
+        self.stack_bufs: set = set()  # buffers that are ONE stacked image [H,W,C] (survivor patches), not [B,H,W,C]
+        self.n_dense_ops: Optional[int] = None  # sparse heads: ops [0, n_dense_ops) run before select/NMS, the rest after
+        self.patch_cap = 0  # sparse heads: patch capacity per level (batch * keep_top_k)
 
     # -- helpers
     def buf(self, name, res, C, fp32=0):
@@ -84,11 +93,19 @@ class Plan:
         self.buf_names[name] = len(self.bufs) - 1
         return len(self.bufs) - 1
 
+    def patch_buf(self, name, C, fp32=0):
+        """Stack of `patch_cap` survivor patches of PATCH x PATCH pixels, stored as one tall image
+        [patch_cap * PATCH, PATCH, C]: a 3x3 conv over the stack is right wherever its window stays inside one patch."""
+        self.bufs.append((self.patch_cap * PATCH, PATCH, C, fp32))
+        self.buf_names[name] = len(self.bufs) - 1
+        self.stack_bufs.add(len(self.bufs) - 1)
+        return len(self.bufs) - 1
+
     def conv(self, label, src, dst, parts, k=1, stride=1, relu=1, res=None, up=0, up_cout=0, cout=None):
         rows = max(p.row + p.cout for p in parts) if not up else 4 * up_cout
         stored = cout if cout is not None else rows
         assert stored % 16 == 0, (label, stored)
-        self.ops.append(Op(_lib.OP_CONV, src, dst, stored, k, stride, relu, up, up_cout, res, parts, 0, label, self.lane))
+        self.ops.append(Op(_lib.OP_CONV, src, dst, stored, k, stride, relu, up, up_cout, res, parts, 0, label, self.lane, self.level))
 
     def simple(self, name, src, dst, cout, k=1, stride=1, relu=1, res=None, cin_logical=None):
         cin = src[2] if cin_logical is None else cin_logical
@@ -121,8 +138,12 @@ class Plan:
             self.simple(name + ".conv3", (cat, 0, 2 * hid), dst, cout)
 
 
-def build_plan(image_size: int = 640) -> Plan:
+def build_plan(image_size: int = 640, sparse_heads: Optional[Tuple[int, int]] = None) -> Plan:
+    """`sparse_heads=(batch, keep_top_k)` builds the two-phase plan: the dense ops end with the box branch; the FLAME
+    branch of every level follows select/NMS and runs on survivor patches (see PATCH)."""
     P = Plan(image_size)
+    if sparse_heads is not None:
+        P.patch_cap = int(sparse_heads[0]) * int(sparse_heads[1])
     S = image_size
     cols = P.buf("stem.cols", S // 2, 32)   # im2col rows of the uint8 image: 27 taps (ky,kx,c) + 5 zeros
     P.ops.append(Op(_lib.OP_STEM, (0, 0, 3), (cols, 0), 32, 3, 2, 0, label="stem.im2col"))
@@ -180,30 +201,22 @@ def build_plan(image_size: int = 640) -> Plan:
     p5 = P.buf("p5", r32, 384)
     P.csp("neck4.csp", (n4_in, 0, 384), (p5, 0), 384, NECKS["neck4"][1], NECKS["neck4"][2], False, r32)
 
-    for l, ((cin, bb, stride), feat) in enumerate(zip(HEADS, (p3, p4, p5)), start=1):
-        h, R = f"head{l}", S // stride
-        lane_a, lane_b, lane_c, lane_d = 1 + 4 * (l - 1), 2 + 4 * (l - 1), 3 + 4 * (l - 1), 4 + 4 * (l - 1)
+    def flame_branch(h, src, R_buf, lanes):
+        """towers0 -> 2 x (shape | expr | transf) -> output convs, reading the pose-stem activations `src`
+        (buf, coff); buffers come from R_buf(name, C, fp32)."""
+        lane_a, lane_b, lane_c = lanes
         P.lane = lane_a
-        st = P.buf(h + ".stems", R, bb + FLAME_INTER)
-        P.conv(h + ".stems", (feat, 0, cin), (st, 0),
-               [Part(h + ".bbox_stem", 0, bb, [(0, 0, cin)]), Part(h + ".pose_stem", bb, FLAME_INTER, [(0, 0, cin)])])
-        P.lane = lane_d   # box branch: cls|reg -> preds
-        cr = P.buf(h + ".clsreg", R, 2 * bb)
-        P.conv(h + ".cls|reg", (st, 0, bb), (cr, 0),
-               [Part(h + ".cls_conv", 0, bb, [(0, 0, bb)]), Part(h + ".reg_conv", bb, bb, [(0, 0, bb)])], k=3)
-        reg = P.buf(h + ".reg_raw", R, REG_ROWS, fp32=1)
-        P.conv(h + ".preds", (cr, 0, 2 * bb), (reg, 0),
-               [Part(h + ".reg_pred", 0, 68, [(bb, 0, bb)]), Part(h + ".cls_pred", 68, 1, [(0, 0, bb)])], relu=0, cout=REG_ROWS)
-        P.reg_buf.append(reg)
-        P.lane = lane_a   # flame branch
-        t_prev = P.buf(h + ".t0", R, 512)
+        t_prev = R_buf(h + ".t0", 512)
         parts, row = [], 0
         for tower, inter, _ in TOWERS:
             parts.append(Part(f"{h}.{tower}.0", row, inter, [(0, 0, FLAME_INTER)]))
             row += inter
-        P.conv(h + ".towers0", (st, bb, FLAME_INTER), (t_prev, 0), parts, k=3)
+        P.conv(h + ".towers0", (src[0], src[1], FLAME_INTER), (t_prev, 0), parts, k=3)
         for i in (1, 2):
-            t_next = P.buf(f"{h}.t{i}", R, 512)
+            if P.level:  # the conv padding of the dense graph: activations outside the image are zero for the next 3x3
+                P.lane = lane_a
+                P.ops.append(Op(_lib.OP_PATCH_MASK, (t_prev, 0, 512), (t_prev, 0), 512, label=f"{h}.mask.t{i - 1}", lane=lane_a, level=P.level))
+            t_next = R_buf(f"{h}.t{i}", 512)
             P.lane = lane_a
             P.simple(f"{h}.shape.{i}", (t_prev, 0, 256), (t_next, 0), 256, k=3)
             P.lane = lane_b
@@ -213,12 +226,49 @@ def build_plan(image_size: int = 640) -> Plan:
                    [Part(f"{h}.{tw}.{i}", 32 * q, 32, [(32 * q, 0, 32)]) for q, tw in enumerate(("rot", "jaw", "scale", "transl"))], k=3)
             t_prev = t_next
         P.lane = lane_a
-        fl = P.buf(h + ".flame_raw", R, FLAME_ROWS, fp32=1)
+        fl = R_buf(h + ".flame_raw", FLAME_ROWS, 1)
         col = {"shape": (0, 256), "expr": (256, 128), "rot": (384, 32), "jaw": (416, 32), "scale": (448, 32), "transl": (480, 32)}
         P.conv(h + ".flame_out", (t_prev, 0, 512), (fl, 0),
                [Part(f"{h}.{tw}.out", RAW_ROW_OFF[tw], oc, [(col[tw][0], 0, col[tw][1])]) for tw, _, oc in TOWERS],
                relu=0, cout=FLAME_ROWS)
         P.flame_buf.append(fl)
+
+    sparse = sparse_heads is not None
+    for l, ((cin, bb, stride), feat) in enumerate(zip(HEADS, (p3, p4, p5)), start=1):
+        h, R = f"head{l}", S // stride
+        lane_a, lane_b, lane_c, lane_d = 1 + 4 * (l - 1), 2 + 4 * (l - 1), 3 + 4 * (l - 1), 4 + 4 * (l - 1)
+        P.lane = lane_a
+        if sparse:   # dense part: the box branch only
+            st = P.buf(h + ".stems", R, bb)
+            P.conv(h + ".bbox_stem", (feat, 0, cin), (st, 0), [Part(h + ".bbox_stem", 0, bb, [(0, 0, cin)])])
+        else:
+            st = P.buf(h + ".stems", R, bb + FLAME_INTER)
+            P.conv(h + ".stems", (feat, 0, cin), (st, 0),
+                   [Part(h + ".bbox_stem", 0, bb, [(0, 0, cin)]), Part(h + ".pose_stem", bb, FLAME_INTER, [(0, 0, cin)])])
+        P.lane = lane_d   # box branch: cls|reg -> preds
+        cr = P.buf(h + ".clsreg", R, 2 * bb)
+        P.conv(h + ".cls|reg", (st, 0, bb), (cr, 0),
+               [Part(h + ".cls_conv", 0, bb, [(0, 0, bb)]), Part(h + ".reg_conv", bb, bb, [(0, 0, bb)])], k=3)
+        reg = P.buf(h + ".reg_raw", R, REG_ROWS, fp32=1)
+        P.conv(h + ".preds", (cr, 0, 2 * bb), (reg, 0),
+               [Part(h + ".reg_pred", 0, 68, [(bb, 0, bb)]), Part(h + ".cls_pred", 68, 1, [(0, 0, bb)])], relu=0, cout=REG_ROWS)
+        P.reg_buf.append(reg)
+        if not sparse:
+            flame_branch(h, (st, bb), lambda name, C, fp32=0, R=R: P.buf(name, R, C, fp32), (lane_a, lane_b, lane_c))
+    if sparse:
+        P.lane = 0
+        P.n_dense_ops = len(P.ops)
+        for l, ((cin, bb, stride), feat) in enumerate(zip(HEADS, (p3, p4, p5)), start=1):
+            h = f"head{l}"
+            lanes = (1 + 4 * (l - 1), 2 + 4 * (l - 1), 3 + 4 * (l - 1))
+            P.level, P.lane = l, lanes[0]
+            pin = P.patch_buf(h + ".patch_in", cin)
+            P.ops.append(Op(_lib.OP_PATCH_GATHER, (feat, 0, cin), (pin, 0), cin, label=h + ".patch_gather", lane=lanes[0], level=l))
+            ps = P.patch_buf(h + ".pose_stem", FLAME_INTER)
+            P.conv(h + ".pose_stem", (pin, 0, cin), (ps, 0), [Part(h + ".pose_stem", 0, FLAME_INTER, [(0, 0, cin)])])
+            P.ops.append(Op(_lib.OP_PATCH_MASK, (ps, 0, FLAME_INTER), (ps, 0), FLAME_INTER, label=h + ".mask.pose_stem", lane=lanes[0], level=l))
+            flame_branch(h, (ps, 0), lambda name, C, fp32=0: P.patch_buf(name, C, fp32), lanes)
+        P.level = 0
     P.lane = 0
     return P
 

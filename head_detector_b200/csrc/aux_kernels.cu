@@ -214,8 +214,9 @@ __device__ __forceinline__ float flame_row_value(const float* __restrict__ raw, 
   return __fmul_rn(__fdiv_rn(expf(raw[204]), 0.05f), stride);
 }
 
+// head = packed index of the survivor (sparse heads only; ignored for dense maps)
 __device__ __forceinline__ const float* raw_row(const DecodeLevels& lv, int b, int a, float& ax_s, float& ay_s,
-                                                float& stride) {
+                                                float& stride, int head = -1) {
   int l = 0;
   while (l < 2 && a >= lv.a_off[l + 1]) ++l;
   const int pix = a - lv.a_off[l];
@@ -223,6 +224,10 @@ __device__ __forceinline__ const float* raw_row(const DecodeLevels& lv, int b, i
   stride = lv.stride[l];
   ax_s = (static_cast<float>(pix % W) + 0.5f) * stride;
   ay_s = (static_cast<float>(pix / W) + 0.5f) * stride;
+  if (lv.head_patch != nullptr && head >= 0) {  // centre pixel of the survivor's patch
+    const size_t row = (static_cast<size_t>(lv.head_patch[head]) * kPatch + kPatchC) * kPatch + kPatchC;
+    return lv.flame[l] + row * lv.flame_cstride;
+  }
   return lv.flame[l] + (static_cast<size_t>(b) * lv.hw[l] + pix) * lv.flame_cstride;
 }
 
@@ -274,19 +279,122 @@ __global__ void __launch_bounds__(128) flame_gather_kernel(const DecodeLevels lv
   const int a = keep_idx[b * keep_k + j];
   const int dst = offsets[b] + j;
   float ax_s, ay_s, stride;
-  const float* raw = raw_row(lv, b, a, ax_s, ay_s, stride);
+  const float* raw = raw_row(lv, b, a, ax_s, ay_s, stride, dst);
   float* o = params + static_cast<size_t>(dst) * 413;
   for (int i = threadIdx.x; i < 413; i += blockDim.x) o[i] = flame_row_value(raw, i, ax_s, ay_s, stride);
   if (threadIdx.x < 3) head_xform[dst * 3 + threadIdx.x] = img_xform ? img_xform[b * 3 + threadIdx.x] : (threadIdx.x == 2 ? 1.f : 0.f);
   if (threadIdx.x == 0 && head_img) head_img[dst] = b;
 }
 
-int flame_gather_launch(const DecodeLevels& lv, const int* keep_idx, const int* keep_cnt, int B, int keep_k,
-                        const float* img_xform, int* offsets, int* total, float* params, float* head_xform,
-                        int* head_img, cudaStream_t stream) {
+int head_offsets_launch(const int* keep_cnt, int B, int* offsets, int* total, cudaStream_t stream) {
   head_offsets_kernel<<<1, 1024, 0, stream>>>(keep_cnt, B, offsets, total);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int flame_gather_launch(const DecodeLevels& lv, const int* keep_idx, const int* keep_cnt, int B, int keep_k,
+                        const float* img_xform, const int* offsets, float* params, float* head_xform,
+                        int* head_img, cudaStream_t stream) {
   flame_gather_kernel<<<dim3(keep_k, B), 128, 0, stream>>>(lv, keep_idx, keep_cnt, offsets, keep_k, img_xform, params,
                                                            head_xform, head_img);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+// ---------------------------------------------------------------------------------------- sparse heads
+// One warp walks the survivors image by image, slot by slot (the packed head order) and hands out patch numbers
+// per level with ballot prefix counts: deterministic, image-major patch order on every level.
+__global__ void __launch_bounds__(32) patch_assign_kernel(const DecodeLevels lv, const int* __restrict__ keep_idx,
+                                                          const int* __restrict__ keep_cnt, const int* __restrict__ offsets, int B,
+                                                          int keep_k, int cap, int* __restrict__ head_level,
+                                                          int* __restrict__ head_patch, int* __restrict__ patch_src,
+                                                          int* __restrict__ level_rows) {
+  const int lane = threadIdx.x;
+  int run[3] = {0, 0, 0};
+  for (int b = 0; b < B; ++b) {
+    const int n = min(keep_cnt[b], keep_k);
+    for (int base = 0; base < n; base += 32) {
+      const int j = base + lane;
+      const bool valid = j < n;
+      int l = -1, y = 0, x = 0;
+      if (valid) {
+        const int a = keep_idx[b * keep_k + j];
+        l = 0;
+        while (l < 2 && a >= lv.a_off[l + 1]) ++l;
+        const int pix = a - lv.a_off[l];
+        y = pix / lv.W[l];
+        x = pix - y * lv.W[l];
+      }
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const unsigned m = __ballot_sync(0xffffffffu, l == q);
+        if (l == q) {
+          const int p = run[q] + __popc(m & ((1u << lane) - 1u));
+          if (p < cap) {
+            head_level[offsets[b] + j] = q;
+            head_patch[offsets[b] + j] = p;
+            patch_src[q * cap + p] = (b << 20) | (y << 10) | x;
+          }
+        }
+        run[q] += __popc(m);
+      }
+    }
+  }
+  if (lane < 3) level_rows[lane] = min(run[lane], cap) * kPatch;
+}
+
+int patch_assign_launch(const DecodeLevels& lv, const int* keep_idx, const int* keep_cnt, const int* offsets, int B, int keep_k,
+                        int cap, int* head_level, int* head_patch, int* patch_src, int* level_rows, cudaStream_t stream) {
+  patch_assign_kernel<<<1, 32, 0, stream>>>(lv, keep_idx, keep_cnt, offsets, B, keep_k, cap, head_level, head_patch, patch_src, level_rows);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+// CTA = one patch: kPatch x kPatch pixels x C channels (16-byte vectors) copied from the feature map, zeros outside it
+__global__ void __launch_bounds__(256) patch_gather_kernel(const __nv_bfloat16* __restrict__ feat, int H, int W, int C_total, int coff,
+                                                           int C, __nv_bfloat16* __restrict__ dst, int dst_C, int dst_coff,
+                                                           const int* __restrict__ patch_src, const int* __restrict__ level_rows) {
+  const int p = blockIdx.x;
+  if (p * kPatch >= *level_rows) return;
+  const int src = patch_src[p];
+  const int b = src >> 20, y0 = ((src >> 10) & 1023) - kPatchC, x0 = (src & 1023) - kPatchC;
+  const int vec = C >> 3;  // uint4 = 8 bf16
+  for (int i = threadIdx.x; i < kPatch * kPatch * vec; i += blockDim.x) {
+    const int pix = i / vec, v = i - pix * vec;
+    const int r = pix / kPatch, c = pix - r * kPatch;
+    const int yy = y0 + r, xx = x0 + c;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+      val = __ldg(reinterpret_cast<const uint4*>(feat + ((static_cast<size_t>(b) * H + yy) * W + xx) * C_total + coff) + v);
+    reinterpret_cast<uint4*>(dst + (static_cast<size_t>(p) * kPatch * kPatch + pix) * dst_C + dst_coff)[v] = val;
+  }
+}
+
+int patch_gather_launch(const __nv_bfloat16* feat, int H, int W, int C_total, int coff, int C, __nv_bfloat16* dst, int dst_C,
+                        int dst_coff, const int* patch_src, const int* level_rows, int cap, cudaStream_t stream) {
+  if (C % 8 || C_total % 8 || coff % 8 || dst_C % 8 || dst_coff % 8) return 1;
+  patch_gather_kernel<<<cap, 256, 0, stream>>>(feat, H, W, C_total, coff, C, dst, dst_C, dst_coff, patch_src, level_rows);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+__global__ void __launch_bounds__(128) patch_mask_kernel(__nv_bfloat16* __restrict__ buf, int C_total, int coff, int C, int H, int W,
+                                                         const int* __restrict__ patch_src, const int* __restrict__ level_rows) {
+  const int p = blockIdx.x;
+  if (p * kPatch >= *level_rows) return;
+  const int src = patch_src[p];
+  const int y0 = ((src >> 10) & 1023) - kPatchC, x0 = (src & 1023) - kPatchC;
+  if (y0 >= 0 && x0 >= 0 && y0 + kPatch <= H && x0 + kPatch <= W) return;  // interior patch: nothing lies outside
+  const int vec = C >> 3;
+  for (int i = threadIdx.x; i < kPatch * kPatch * vec; i += blockDim.x) {
+    const int pix = i / vec, v = i - pix * vec;
+    const int r = pix / kPatch, c = pix - r * kPatch;
+    const int yy = y0 + r, xx = x0 + c;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) continue;
+    reinterpret_cast<uint4*>(buf + (static_cast<size_t>(p) * kPatch * kPatch + pix) * C_total + coff)[v] = make_uint4(0, 0, 0, 0);
+  }
+}
+
+int patch_mask_launch(__nv_bfloat16* buf, int C_total, int coff, int C, int H, int W, const int* patch_src,
+                      const int* level_rows, int cap, cudaStream_t stream) {
+  if (C % 8 || C_total % 8 || coff % 8) return 1;
+  patch_mask_kernel<<<cap, 128, 0, stream>>>(buf, C_total, coff, C, H, W, patch_src, level_rows);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

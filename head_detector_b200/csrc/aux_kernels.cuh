@@ -15,14 +15,31 @@ struct DecodeLevels {
   int hw[3];
   float stride[3];
   int reg_cstride, flame_cstride;
+  // sparse heads: flame[l] is the level's patch stack [patches*kPatch, kPatch, flame_cstride]; the row of head h
+  // (packed image-major order) is the centre pixel of patch head_patch[h] of level head_level[h].  Null = dense maps.
+  const int* head_level;
+  const int* head_patch;
 };
+
+constexpr int kPatch = 8, kPatchC = 3;  // survivor patch size / offset of the anchor inside it (arch.py PATCH, PATCH_C)
 
 int stem_pack_launch(const uint8_t* img, __nv_bfloat16* out, int B, int S, cudaStream_t stream);
 int spp_pool_launch(__nv_bfloat16* buf, int B, int H, int W, int C, cudaStream_t stream);
 int box_decode_launch(const DecodeLevels& lv, float* boxes, float* scores, int B, int A, cudaStream_t stream);
 int flame_dense_launch(const DecodeLevels& lv, float* out, int B, int A, cudaStream_t stream);
+int head_offsets_launch(const int* keep_cnt, int B, int* offsets, int* total, cudaStream_t stream);
 int flame_gather_launch(const DecodeLevels& lv, const int* keep_idx, const int* keep_cnt, int B, int keep_k,
-                        const float* img_xform, int* offsets, int* total, float* params, float* head_xform,
+                        const float* img_xform, const int* offsets, float* params, float* head_xform,
                         int* head_img, cudaStream_t stream);
+// sparse heads: survivors -> (level, patch) in image-major order; patch_src[l*cap + p] = image << 20 | y << 10 | x,
+// level_rows[l] = patches of level l * kPatch (the live height of the level's patch stacks)
+int patch_assign_launch(const DecodeLevels& lv, const int* keep_idx, const int* keep_cnt, const int* offsets, int B, int keep_k,
+                        int cap, int* head_level, int* head_patch, int* patch_src, int* level_rows, cudaStream_t stream);
+// feature map [B,H,W,C_total] channels [coff, coff+C) -> patch stack [cap*kPatch, kPatch, dst_C] channels [dst_coff, ..)
+int patch_gather_launch(const __nv_bfloat16* feat, int H, int W, int C_total, int coff, int C, __nv_bfloat16* dst, int dst_C,
+                        int dst_coff, const int* patch_src, const int* level_rows, int cap, cudaStream_t stream);
+// zero the pixels of a patch stack that lie outside the H x W feature map (the dense graph's conv padding)
+int patch_mask_launch(__nv_bfloat16* buf, int C_total, int coff, int C, int H, int W, const int* patch_src,
+                      const int* level_rows, int cap, cudaStream_t stream);
 int copy_rows_launch(const float* src, float* dst, const int* count_ptr, int row_floats, int max_rows, cudaStream_t stream);
 }  // namespace vgh

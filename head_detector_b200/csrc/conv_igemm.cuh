@@ -26,6 +26,7 @@ struct ConvLaunch {
   const float* bias;             // [N_pad]
   void* out;                     // output buffer base (bf16 or fp32)
   const __nv_bfloat16* res;      // residual buffer base or nullptr
+  const int* dyn_rows;           // swapped kernel: device-side live height of a stacked-patch input (rows <= Ho), or nullptr
   int B, Ho, Wo;                 // GEMM-row space: output pixels (before any pixel shuffle)
   int tw, th, tiles_x, tiles_y;  // spatial tile (tw*th <= 128) and tile counts per image
   int cin_off, cin;              // channel coordinate offset / channels per tap (multiple of BK)

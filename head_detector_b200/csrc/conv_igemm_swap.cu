@@ -84,14 +84,15 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int tiles_per_img = p.tiles_x * p.tiles_y;
   // Work items: a cluster (1 or 2 CTAs) walks (tile group of n_cl pixel tiles, channel group); CTA r of the
   // cluster takes tile r of the group.  With n_cl == 1 this is item = tile * ngroups + group as before.
+  // The counts are set after the PDL wait: survivor-patch launches read their live height from device memory.
   const int n_cl = p.cluster;
   const uint32_t cta_rank = n_cl > 1 ? cluster_ctarank() : 0u;
   const int cl_id = blockIdx.x / n_cl, n_cls = gridDim.x / n_cl;
-  const int total_tiles = tiles_per_img * p.B;
-  const int n_citems = ((total_tiles + n_cl - 1) / n_cl) * p.ngroups;
+  int tiles_per_img = p.tiles_x * p.tiles_y;
+  int total_tiles = tiles_per_img * p.B;
+  int n_citems = ((total_tiles + n_cl - 1) / n_cl) * p.ngroups;
   // -> tile (clamped; `valid` false for the filler tile of an odd tile count: computed, never stored), group base
   auto item_tile = [&](int ci, int& tile, int& n_base) -> bool {
     const int tg = ci / p.ngroups;
@@ -137,6 +138,12 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
   // everything above overlapped the previous kernel's tail (PDL); its outputs are needed from here on
   pdl_wait();
   pdl_launch_dependents();
+  if (p.dyn_rows != nullptr) {  // stacked survivor patches (one tall image): only the first *dyn_rows rows are live
+    const int rows = min(__ldg(p.dyn_rows), p.Ho);
+    tiles_per_img = p.tiles_x * ((rows + p.th - 1) / p.th);
+    total_tiles = tiles_per_img * p.B;
+    n_citems = ((total_tiles + n_cl - 1) / n_cl) * p.ngroups;
+  }
 
   const int cblks = p.cin / BK;
   const int num_kb = p.ntaps * cblks;

@@ -114,6 +114,10 @@ struct vgh_detector {
   int *keep_idx = nullptr, *keep_cnt = nullptr, *offsets = nullptr, *head_img = nullptr;
   float *params = nullptr, *head_xform = nullptr, *verts = nullptr, *rot = nullptr, *img_xform = nullptr;
   const float *ovr_boxes = nullptr, *ovr_scores = nullptr;
+  // sparse heads: ops [n_dense_ops, n) run after select/NMS on survivor patches (one stack per head level)
+  int n_dense_ops = 0, patch_cap = 0;
+  bool sparse = false;
+  int *head_level = nullptr, *head_patch = nullptr, *patch_src = nullptr, *level_rows = nullptr;
   cudaGraphExec_t graph = nullptr;
   cudaStream_t cap_stream = nullptr;  // capture needs a non-legacy stream; the graph then replays anywhere
   // two-deep host pipeline (vgh_detector_submit_host / collect_host)
@@ -128,6 +132,7 @@ struct vgh_detector {
   int submit_idx = 0, collect_idx = 0;
   std::vector<cudaStream_t> lane_streams;  // side streams for independent graph branches (lanes 1..)
   std::vector<cudaEvent_t> op_events;
+  cudaEvent_t phase_event = nullptr;
   bool multi_lane = true;
   float g_conf = -1.f, g_iou = -1.f;
   int g_topk = -1;
@@ -250,12 +255,20 @@ static int build_conv(vgh_detector* d, OpRt& o) {
   if (q.cin % 32) return fail(2, "cin %d not a multiple of 32", q.cin);
   o.bk = q.cin % 64 == 0 ? 64 : 32;
   L.B = d->B;
+  const bool patch_op = q.level > 0;  // survivor patches: one stacked image whose live height is known on the device only
+  if (patch_op) {
+    if (!ib.stack || !ob.stack || q.level > 3 || q.stride != 1 || q.up || !swap_eligible(q, ob))
+      return fail(2, "patch-level conv must map stacked buffers, stride 1, and be eligible for the swapped kernel");
+    L.B = 1;
+  } else if (ib.stack || ob.stack) {
+    return fail(2, "dense op on a stacked buffer");
+  }
   L.stride = q.stride;
   L.Ho = q.up ? ib.H : (ib.H + q.stride - 1) / q.stride;
   L.Wo = q.up ? ib.W : (ib.W + q.stride - 1) / q.stride;
   // un-tuned default: the swapped kernel for Cout <= 128 on large maps and - with the tap reuse, which measured
   // faster than every other variant on every 3x3 stride-1 layer of the network - for all of those
-  L.swap = o.cfg_swap >= 0 ? o.cfg_swap
+  L.swap = patch_op ? 1 : o.cfg_swap >= 0 ? o.cfg_swap
                            : (swap_eligible(q, ob) && (swap_forced() || (xr_eligible(q, ob) && xr_default()) ||
                                                        (q.cout <= 128 && !ob.fp32 && L.Ho * L.Wo >= 1024)) ? 1 : 0);
   if (L.swap) swap_groups(q, ob, L.ngroups, L.gw);
@@ -308,6 +321,7 @@ static int build_conv(vgh_detector* d, OpRt& o) {
   }
   L.bias = d->bias + q.b_off;
   L.out = d->buf_ptr[q.out_buf];
+  L.dyn_rows = patch_op ? d->level_rows + (q.level - 1) : nullptr;
   if (q.res_buf >= 0) {
     const vgh_buf_desc& rb = d->bufs[q.res_buf];
     if (rb.H != L.Ho || rb.W != L.Wo || rb.fp32) return fail(2, "residual buffer mismatch");
@@ -370,10 +384,11 @@ extern "C" void vgh_detector_destroy(vgh_detector* d) {
   for (cudaStream_t t : {d->h2d_stream, d->d2h_stream, d->pipe_stream}) if (t) cudaStreamDestroy(t);
   for (cudaStream_t t : d->lane_streams) cudaStreamDestroy(t);
   for (cudaEvent_t e : d->op_events) if (e) cudaEventDestroy(e);
+  if (d->phase_event) cudaEventDestroy(d->phase_event);
   for (void* p : d->buf_ptr) cudaFree(p);
   void* ptrs[] = {d->weights, d->bias, d->input, d->boxes, d->scores, d->keep_boxes,
                   d->keep_scores, d->keep_idx, d->keep_cnt, d->offsets, d->head_img, d->params, d->head_xform,
-                  d->verts, d->rot, d->img_xform};
+                  d->verts, d->rot, d->img_xform, d->head_level, d->head_patch, d->patch_src, d->level_rows};
   for (void* p : ptrs) cudaFree(p);
   delete d;
 }
@@ -403,8 +418,15 @@ extern "C" int vgh_detector_create(const vgh_net_desc* n, const vgh_flame* flame
   auto bail = [&](int code) { vgh_detector_destroy(d); return code; };
 
   d->bufs.assign(n->bufs, n->bufs + n->n_bufs);
+  d->n_dense_ops = (n->n_dense_ops > 0 && n->n_dense_ops < n->n_ops) ? n->n_dense_ops : n->n_ops;
+  d->sparse = d->n_dense_ops < n->n_ops;
+  d->patch_cap = d->B * d->keep_k;
+  if (d->sparse && (dmalloc(&d->head_level, (size_t)d->patch_cap) != cudaSuccess || dmalloc(&d->head_patch, (size_t)d->patch_cap) != cudaSuccess ||
+                    dmalloc(&d->patch_src, (size_t)3 * d->patch_cap) != cudaSuccess || dmalloc(&d->level_rows, 4) != cudaSuccess))
+    return bail(fail(4, "patch table allocation failed"));
   for (const vgh_buf_desc& b : d->bufs) {
-    const size_t bytes = static_cast<size_t>(d->B) * b.H * b.W * b.C * (b.fp32 ? 4 : 2);
+    if (b.stack && (b.W != kPatch || b.H != d->patch_cap * kPatch)) return bail(fail(2, "stacked buffer must be [batch*keep_k*%d, %d, C]", kPatch, kPatch));
+    const size_t bytes = static_cast<size_t>(b.stack ? 1 : d->B) * b.H * b.W * b.C * (b.fp32 ? 4 : 2);
     void* p = nullptr;
     if (cudaMalloc(&p, bytes) != cudaSuccess || cudaMemset(p, 0, bytes) != cudaSuccess)
       return bail(fail(4, "activation buffer allocation failed (%zu bytes)", bytes));
@@ -424,6 +446,7 @@ extern "C" int vgh_detector_create(const vgh_net_desc* n, const vgh_flame* flame
       rc = build_conv(d, o);
       if (rc) return bail(rc);
     }
+    if ((o.d.level > 0) != (i >= d->n_dense_ops)) return bail(fail(2, "op %d: patch-level ops must be exactly the ops after n_dense_ops", i));
     d->ops.push_back(o);
   }
   // decode bookkeeping
@@ -431,7 +454,7 @@ extern "C" int vgh_detector_create(const vgh_net_desc* n, const vgh_flame* flame
   for (int l = 0; l < 3; ++l) {
     const vgh_buf_desc& rb = d->bufs[n->reg_buf[l]];
     const vgh_buf_desc& fb = d->bufs[n->flame_buf[l]];
-    if (!rb.fp32 || !fb.fp32 || rb.H != fb.H) return bail(fail(2, "raw head buffers must be fp32"));
+    if (!rb.fp32 || !fb.fp32 || (rb.H != fb.H && !fb.stack) || (fb.stack != 0) != d->sparse) return bail(fail(2, "raw head buffers must be fp32 (flame: dense map, or patch stack in a sparse plan)"));
     d->lv.reg[l] = static_cast<const float*>(d->buf_ptr[n->reg_buf[l]]);
     d->lv.flame[l] = static_cast<const float*>(d->buf_ptr[n->flame_buf[l]]);
     d->lv.a_off[l] = a_off;
@@ -443,6 +466,8 @@ extern "C" int vgh_detector_create(const vgh_net_desc* n, const vgh_flame* flame
     a_off += rb.H * rb.W;
   }
   d->lv.a_off[3] = a_off;
+  d->lv.head_level = d->sparse ? d->head_level : nullptr;
+  d->lv.head_patch = d->sparse ? d->head_patch : nullptr;
   d->A = a_off;
   const size_t B = d->B, A = d->A, K = d->keep_k, cap = B * K;
   if (dmalloc(&d->input, B * d->S * d->S * 3) != cudaSuccess || dmalloc(&d->boxes, B * A * 4) != cudaSuccess ||
@@ -480,6 +505,24 @@ static int launch_op(vgh_detector* d, OpRt& o, const uint8_t* images, cudaStream
       if (rc) return fail(5, "spp launch failed");
       break;
     }
+    case VGH_OP_PATCH_GATHER: {
+      const vgh_buf_desc& fb = d->bufs[o.d.in_buf];
+      const vgh_buf_desc& pb = d->bufs[o.d.out_buf];
+      const int l = o.d.level - 1;
+      rc = patch_gather_launch(static_cast<const __nv_bfloat16*>(d->buf_ptr[o.d.in_buf]), fb.H, fb.W, fb.C, o.d.in_coff, o.d.cin,
+                               static_cast<__nv_bfloat16*>(d->buf_ptr[o.d.out_buf]), pb.C, o.d.out_coff,
+                               d->patch_src + static_cast<size_t>(l) * d->patch_cap, d->level_rows + l, d->patch_cap, s);
+      if (rc) return fail(5, "patch gather launch failed");
+      break;
+    }
+    case VGH_OP_PATCH_MASK: {
+      const vgh_buf_desc& pb = d->bufs[o.d.out_buf];
+      const int l = o.d.level - 1;
+      rc = patch_mask_launch(static_cast<__nv_bfloat16*>(d->buf_ptr[o.d.out_buf]), pb.C, o.d.out_coff, o.d.cin, d->lv.hw[l] / d->lv.W[l],
+                             d->lv.W[l], d->patch_src + static_cast<size_t>(l) * d->patch_cap, d->level_rows + l, d->patch_cap, s);
+      if (rc) return fail(5, "patch mask launch failed");
+      break;
+    }
     default:
       return fail(5, "unknown op kind %d", o.d.kind);
   }
@@ -491,7 +534,7 @@ static int launch_op(vgh_detector* d, OpRt& o, const uint8_t* images, cudaStream
 // pipeline fill/drain of one kernel is covered by CTAs of another; cross-lane ordering comes from
 // buffer-level dependency tracking (RAW / WAR / WAW per activation buffer), expressed as events -
 // which CUDA-graph capture turns into graph edges.
-static int run_forward(vgh_detector* d, const uint8_t* images, cudaStream_t s, int* launches) {
+static int run_ops(vgh_detector* d, int op_begin, int op_end, const uint8_t* images, cudaStream_t s, int* launches) {
   const int n_ops = static_cast<int>(d->ops.size());
   const int n_bufs = static_cast<int>(d->bufs.size());
   if (d->op_events.size() < static_cast<size_t>(n_ops)) {
@@ -511,6 +554,11 @@ static int run_forward(vgh_detector* d, const uint8_t* images, cudaStream_t s, i
   std::vector<int> last_w(static_cast<size_t>(n_bufs) * L, -1), last_r(static_cast<size_t>(n_bufs) * L, -1);
   std::vector<char> recorded(n_ops, 0);
   std::vector<int> last_op_on_lane(L, -1);
+  if (L > 1 && op_begin > 0) {  // later phase: whatever lane 0 has queued so far (select/NMS, patch tables) precedes every lane
+    if (!d->phase_event) CUDA_OK(cudaEventCreateWithFlags(&d->phase_event, cudaEventDisableTiming));
+    CUDA_OK(cudaEventRecord(d->phase_event, s));
+    for (int l2 = 1; l2 < L; ++l2) CUDA_OK(cudaStreamWaitEvent(stream_of(l2), d->phase_event, 0));
+  }
   auto depend = [&](int lane, int op_j) -> int {  // lane must wait for op_j (which ran on another lane)
     if (op_j < 0) return 0;
     const int lj = d->multi_lane ? d->ops[op_j].d.lane : 0;
@@ -522,11 +570,11 @@ static int run_forward(vgh_detector* d, const uint8_t* images, cudaStream_t s, i
     CUDA_OK(cudaStreamWaitEvent(stream_of(lane), d->op_events[op_j], 0));
     return 0;
   };
-  for (int i = 0; i < n_ops; ++i) {
+  for (int i = op_begin; i < op_end; ++i) {
     OpRt& o = d->ops[i];
     const int lane = d->multi_lane ? o.d.lane : 0;
     if (L > 1) {
-      int reads[2] = {o.d.kind == VGH_OP_STEM ? -1 : o.d.in_buf, o.d.res_buf};
+      int reads[2] = {o.d.kind == VGH_OP_STEM ? -1 : o.d.in_buf, o.d.kind == VGH_OP_CONV ? o.d.res_buf : -1};
       for (int b : reads) {
         if (b < 0) continue;
         for (int l2 = 0; l2 < L; ++l2) { int rc = depend(lane, last_w[b * L + l2]); if (rc) return rc; }
@@ -550,6 +598,12 @@ static int run_forward(vgh_detector* d, const uint8_t* images, cudaStream_t s, i
     int rc = depend(0, last_op_on_lane[l2]);
     if (rc) return rc;
   }
+  return 0;
+}
+
+static int run_forward(vgh_detector* d, const uint8_t* images, cudaStream_t s, int* launches) {
+  int rc = run_ops(d, 0, d->n_dense_ops, images, s, launches);
+  if (rc) return rc;
   if (box_decode_launch(d->lv, d->boxes, d->scores, d->B, d->A, s)) return fail(5, "box decode launch failed");
   if (launches) ++*launches;
   if (d->ovr_boxes && d->ovr_scores) {
@@ -563,8 +617,17 @@ static int run_post(vgh_detector* d, float conf, float iou, int top_k, const flo
   int rc = select_nms_launch(d->boxes, d->scores, d->B, d->A, conf, iou, top_k, d->keep_k, d->keep_idx, d->keep_cnt,
                              d->keep_boxes, d->keep_scores, s, g_err, sizeof(g_err));
   if (rc) return rc;
-  if (flame_gather_launch(d->lv, d->keep_idx, d->keep_cnt, d->B, d->keep_k, xform, d->offsets, d->offsets + d->B,
-                          d->params, d->head_xform, d->head_img, s))
+  if (head_offsets_launch(d->keep_cnt, d->B, d->offsets, d->offsets + d->B, s)) return fail(5, "offsets launch failed");
+  if (d->sparse) {  // FLAME branch of the heads on survivor patches only
+    if (patch_assign_launch(d->lv, d->keep_idx, d->keep_cnt, d->offsets, d->B, d->keep_k, d->patch_cap, d->head_level,
+                            d->head_patch, d->patch_src, d->level_rows, s))
+      return fail(5, "patch assign launch failed");
+    if (launches) ++*launches;
+    rc = run_ops(d, d->n_dense_ops, static_cast<int>(d->ops.size()), nullptr, s, launches);
+    if (rc) return rc;
+  }
+  if (flame_gather_launch(d->lv, d->keep_idx, d->keep_cnt, d->B, d->keep_k, xform, d->offsets, d->params, d->head_xform,
+                          d->head_img, s))
     return fail(5, "gather launch failed");
   if (launches) *launches += 3;
   if (d->flame) {
@@ -587,6 +650,13 @@ extern "C" int vgh_detector_autotune(vgh_detector* d, int iters, void* stream) {
   CUDA_OK(cudaEventCreate(&e0));
   CUDA_OK(cudaEventCreate(&e1));
   if (iters < 1) iters = 3;
+  // patch-level convs are tuned at a nominal load of 8 survivors per image spread over the three head levels
+  const int nominal_rows[4] = {d->B * 4 * kPatch, d->B * 3 * kPatch, d->B * 2 * kPatch, 0};
+  int saved_rows[4] = {0, 0, 0, 0};
+  if (d->sparse) {
+    CUDA_OK(cudaMemcpy(saved_rows, d->level_rows, sizeof(saved_rows), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(d->level_rows, nominal_rows, sizeof(nominal_rows), cudaMemcpyHostToDevice));
+  }
   for (OpRt& o : d->ops) {
     if (o.d.kind != VGH_OP_CONV) continue;
     float best = 1e30f;
@@ -671,7 +741,7 @@ extern "C" int vgh_detector_autotune(vgh_detector* d, int iters, void* stream) {
       }
     }
     for (int mt : {1, 2, 4}) {
-      if (mt * bn > 512) continue;
+      if (mt * bn > 512 || o.d.level > 0) continue;  // patch-level convs: swapped kernel only
       for (int variant = 0; variant < 2; ++variant) {
         OpRt t = o;
         t.cfg_swap = 0; t.cfg_tw = 0; t.cfg_th = 0;
@@ -713,6 +783,7 @@ extern "C" int vgh_detector_autotune(vgh_detector* d, int iters, void* stream) {
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
+  if (d->sparse) CUDA_OK(cudaMemcpy(d->level_rows, saved_rows, sizeof(saved_rows), cudaMemcpyHostToDevice));
   return 0;
 }
 // Reports the configuration of conv op i: out[0..5] = mt, stages, block_n, bk, tw, th.
@@ -725,7 +796,8 @@ extern "C" int vgh_detector_op_config(const vgh_detector* d, int op, int32_t* ou
   return 0;
 }
 
-// Eager execution with one CUDA-event pair around every plan op and every post-processing stage.
+// Eager execution with one CUDA-event pair around every plan op and every post-processing stage (in execution
+// order: dense ops, box decode, select/NMS, [sparse heads: patch tables + patch ops], survivor rows, FLAME decode).
 extern "C" int vgh_detector_profile(vgh_detector* d, int iters, float conf_thr, float iou_thr, int top_k,
                                     float* ms_out, int capacity, void* stream) {
   if (!d || !ms_out || iters < 1) return fail(1, "bad argument");
@@ -733,47 +805,65 @@ extern "C" int vgh_detector_profile(vgh_detector* d, int iters, float conf_thr, 
   const int n_ops = static_cast<int>(d->ops.size());
   const int n = n_ops + 4;
   if (capacity < n) return fail(1, "ms_out capacity %d < %d", capacity, n);
-  std::vector<cudaEvent_t> ev(n + 1);
-  for (auto& e : ev) CUDA_OK(cudaEventCreate(&e));
+  std::vector<cudaEvent_t> e0(n), e1(n);
+  for (auto& e : e0) CUDA_OK(cudaEventCreate(&e));
+  for (auto& e : e1) CUDA_OK(cudaEventCreate(&e));
   std::vector<double> acc(n, 0.0);
   int rc = 0;
-  for (int it = 0; it < iters && !rc; ++it) {
-    CUDA_OK(cudaEventRecord(ev[0], s));
-    for (int i = 0; i < n_ops && !rc; ++i) {
-      OpRt& o = d->ops[i];
-      if (o.d.kind == VGH_OP_STEM)
-        rc = stem_pack_launch(d->input, static_cast<__nv_bfloat16*>(d->buf_ptr[o.d.out_buf]), d->B, d->S, s);
-      else if (o.d.kind == VGH_OP_CONV)
-        rc = conv_launch(o.L, o.bk, s);
-      else
-        rc = spp_pool_launch(static_cast<__nv_bfloat16*>(d->buf_ptr[o.d.in_buf]), d->B, d->bufs[o.d.in_buf].H, d->bufs[o.d.in_buf].W, o.d.cin, s);
-      CUDA_OK(cudaEventRecord(ev[i + 1], s));
+  auto timed_ops = [&](int begin, int end) {
+    for (int i = begin; i < end && !rc; ++i) {
+      cudaEventRecord(e0[i], s);
+      rc = launch_op(d, d->ops[i], d->input, s);
+      cudaEventRecord(e1[i], s);
     }
+  };
+  for (int it = 0; it < iters && !rc; ++it) {
+    timed_ops(0, d->n_dense_ops);
     if (rc) break;
+    cudaEventRecord(e0[n_ops], s);
     rc = box_decode_launch(d->lv, d->boxes, d->scores, d->B, d->A, s);
     if (d->ovr_boxes && d->ovr_scores) {
       cudaMemcpyAsync(d->boxes, d->ovr_boxes, sizeof(float) * 4 * d->B * d->A, cudaMemcpyDeviceToDevice, s);
       cudaMemcpyAsync(d->scores, d->ovr_scores, sizeof(float) * d->B * d->A, cudaMemcpyDeviceToDevice, s);
     }
-    CUDA_OK(cudaEventRecord(ev[n_ops + 1], s));
+    cudaEventRecord(e1[n_ops], s);
+    cudaEventRecord(e0[n_ops + 1], s);
     if (!rc) rc = select_nms_launch(d->boxes, d->scores, d->B, d->A, conf_thr, iou_thr, top_k, d->keep_k, d->keep_idx, d->keep_cnt,
                                     d->keep_boxes, d->keep_scores, s, g_err, sizeof(g_err));
-    CUDA_OK(cudaEventRecord(ev[n_ops + 2], s));
-    if (!rc) rc = flame_gather_launch(d->lv, d->keep_idx, d->keep_cnt, d->B, d->keep_k, d->img_xform, d->offsets, d->offsets + d->B,
-                                      d->params, d->head_xform, d->head_img, s);
-    CUDA_OK(cudaEventRecord(ev[n_ops + 3], s));
+    cudaEventRecord(e1[n_ops + 1], s);
+    cudaEventRecord(e0[n_ops + 2], s);  // "gather" = head offsets (+ patch tables) ... survivor rows, without the patch ops
+    if (!rc) rc = head_offsets_launch(d->keep_cnt, d->B, d->offsets, d->offsets + d->B, s);
+    if (!rc && d->sparse)
+      rc = patch_assign_launch(d->lv, d->keep_idx, d->keep_cnt, d->offsets, d->B, d->keep_k, d->patch_cap, d->head_level, d->head_patch,
+                               d->patch_src, d->level_rows, s);
+    cudaEventRecord(e1[n_ops + 2], s);
+    if (!rc) timed_ops(d->n_dense_ops, n_ops);
+    cudaEvent_t g0, g1;
+    CUDA_OK(cudaEventCreate(&g0));
+    CUDA_OK(cudaEventCreate(&g1));
+    cudaEventRecord(g0, s);
+    if (!rc) rc = flame_gather_launch(d->lv, d->keep_idx, d->keep_cnt, d->B, d->keep_k, d->img_xform, d->offsets, d->params,
+                                      d->head_xform, d->head_img, s);
+    cudaEventRecord(g1, s);
+    cudaEventRecord(e0[n_ops + 3], s);
     if (!rc && d->flame)
       rc = flame_decode_launch(d->flame->model, d->params, d->B * d->keep_k, d->offsets + d->B, 128, 64, d->head_xform, nullptr,
                                d->rot, d->verts, s, g_err, sizeof(g_err));
-    CUDA_OK(cudaEventRecord(ev[n_ops + 4], s));
+    cudaEventRecord(e1[n_ops + 3], s);
     CUDA_OK(cudaStreamSynchronize(s));
     for (int i = 0; i < n; ++i) {
       float ms = 0.f;
-      cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+      cudaEventElapsedTime(&ms, e0[i], e1[i]);
       acc[i] += ms;
     }
+    float gms = 0.f;
+    cudaEventElapsedTime(&gms, g0, g1);
+    acc[n_ops + 2] += gms;
+    cudaEventDestroy(g0);
+    cudaEventDestroy(g1);
   }
-  for (auto& e : ev) cudaEventDestroy(e);
+  for (auto& e : e0) cudaEventDestroy(e);
+  for (auto& e : e1) cudaEventDestroy(e);
   if (rc) return rc > 0 && g_err[0] ? rc : fail(5, "profile launch failed");
   for (int i = 0; i < n; ++i) ms_out[i] = static_cast<float>(acc[i] / iters);
   return 0;
@@ -791,6 +881,7 @@ extern "C" int vgh_detector_postprocess(vgh_detector* d, float conf_thr, float i
 }
 extern "C" int vgh_detector_dense_flame(vgh_detector* d, float* flame_dev, void* stream) {
   if (!d || !flame_dev) return fail(1, "null argument");
+  if (d->sparse) return fail(2, "the dense [B,A,413] tensor does not exist in a sparse-heads plan (FLAME branch runs on survivors only)");
   return flame_dense_launch(d->lv, flame_dev, d->B, d->A, static_cast<cudaStream_t>(stream)) ? fail(5, "dense flame launch failed") : 0;
 }
 extern "C" void* vgh_detector_output(vgh_detector* d, int which) {

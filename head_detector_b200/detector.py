@@ -8,7 +8,9 @@ Differences that are extensions, not changes: `weights=` (a deploy-form weight d
 torch-saved one; the HF download of detector.py:25-30 is impossible offline), `batch_size=` and
 `detect_batch()` (batched semantics of yolo_heads_post_prediction_callback.py:55-97), and
 `device_letterbox=` (default True: `_transform_image` runs as one CUDA kernel for the whole batch,
-bit-exact with the cv2 calls of detector.py:47-50; False keeps the reference's host cv2 path)."""
+bit-exact with the cv2 calls of detector.py:47-50; False keeps the reference's host cv2 path) and
+`sparse_heads=` (default True: the FLAME branch of the detection heads is evaluated after NMS on 8x8
+windows around the surviving anchors instead of on the whole feature maps - same heads, same numbers)."""
 import os
 import warnings
 from typing import Any, Dict, List, Optional, Tuple, Union
@@ -27,7 +29,7 @@ from .utils import rpy_from_rotations
 
 class HeadDetector:
     def __init__(self, model: str = "vgg_heads_l", image_size: int = 640, weights: Union[None, str, Dict[str, torch.Tensor]] = None,
-                 batch_size: int = 1, keep_top_k: int = 100, device_letterbox: bool = True):
+                 batch_size: int = 1, keep_top_k: int = 100, device_letterbox: bool = True, sparse_heads: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("head_detector_b200.HeadDetector needs a CUDA device (sm_100a); there is no CPU fallback")
         self._image_size = image_size
@@ -36,6 +38,7 @@ class HeadDetector:
         self._batch = batch_size
         self._keep_top_k = keep_top_k
         self._device_letterbox = device_letterbox
+        self._sparse_heads = sparse_heads   # FLAME branch of the heads on the NMS survivors only (same predictions)
         self.model = self._read_model(model, weights)
 
     def _read_model(self, model: str, weights=None) -> Engine:
@@ -49,7 +52,7 @@ class HeadDetector:
             warnings.warn("no weights given and the released vgg_heads_l checkpoint is unreachable offline: "
                           "using seeded random-init weights (architecture and cost are exact, detections are not meaningful)")
             weights = arch.synthetic_weights(0)
-        return Engine(weights, self._batch, self._image_size, self._keep_top_k, self._flame)
+        return Engine(weights, self._batch, self._image_size, self._keep_top_k, self._flame, sparse_heads=self._sparse_heads)
 
     # -- host-side pre-processing, same arithmetic as detector.py:32-56
     def _convert_image(self, image) -> np.ndarray:

@@ -18,15 +18,24 @@ class _DevView:
 
 class Engine:
     def __init__(self, weights: Dict[str, torch.Tensor], batch: int, image_size: int = 640, keep_top_k: int = 100,
-                 flame: Optional[FLAMELayer] = None):
+                 flame: Optional[FLAMELayer] = None, sparse_heads: Optional[bool] = None):
+        """`sparse_heads`: run the FLAME branch of the three head levels on 8x8 windows around the NMS survivors
+        instead of the whole feature maps (same values at the survivors; the dense [B,A,413] tensor of the
+        reference's model boundary then does not exist).  Default: $VGGHEADS_B200_SPARSE_HEADS == "1"."""
         if not torch.cuda.is_available():
             raise RuntimeError("head_detector_b200.Engine needs a CUDA device (no CPU fallback)")
         self.B, self.S, self.keep_k = int(batch), int(image_size), int(keep_top_k)
         self.flame = flame if flame is not None else FLAMELayer()
-        self.plan = arch.build_plan(self.S)
+        if sparse_heads is None:
+            import os
+
+            sparse_heads = os.environ.get("VGGHEADS_B200_SPARSE_HEADS", "0") == "1"
+        self.sparse_heads = bool(sparse_heads)
+        self.plan = arch.build_plan(self.S, sparse_heads=(self.B, self.keep_k) if self.sparse_heads else None)
         self.packed = arch.pack(self.plan, weights)
         pk = self.packed
-        bufs = (_lib.BufDesc * len(self.plan.bufs))(*[_lib.BufDesc(*b) for b in self.plan.bufs])
+        bufs = (_lib.BufDesc * len(self.plan.bufs))(*[_lib.BufDesc(*b, 1 if i in self.plan.stack_bufs else 0)
+                                                       for i, b in enumerate(self.plan.bufs)])
         ops = (_lib.OpDesc * len(self.plan.ops))()
         for o, op, m in zip(ops, self.plan.ops, pk.op_meta):
             o.kind = op.kind
@@ -35,6 +44,7 @@ class Engine:
             o.cout, o.ksize, o.stride, o.relu, o.up, o.up_cout = op.cout, op.k, op.stride, op.relu, op.up, op.up_cout
             o.res_buf, o.res_coff = (op.res[0], op.res[1]) if op.res is not None else (-1, 0)
             o.lane = op.lane
+            o.level = op.level
             if m:
                 o.res_alpha, o.n_pad, o.k_total, o.block_n = m["alpha"], m["n_pad"], m["k_total"], m["block_n"]
                 o.w_off, o.b_off = m["w_off"], m["b_off"]
@@ -46,6 +56,7 @@ class Engine:
         nd.reg_buf = (C.c_int32 * 3)(*self.plan.reg_buf)
         nd.flame_buf = (C.c_int32 * 3)(*self.plan.flame_buf)
         nd.keep_k = self.keep_k
+        nd.n_dense_ops = self.plan.n_dense_ops if self.plan.n_dense_ops is not None else len(self.plan.ops)
         h = C.c_void_p()
         _lib.check(_lib.lib().vgh_detector_create(C.byref(nd), self.flame.handle(), C.byref(h)), "vgh_detector_create")
         self._h = h
@@ -183,10 +194,11 @@ class Engine:
         """Activation buffer by plan name -> float32 NHWC cpu tensor (debug / layer-wise parity)."""
         i = self.plan.buf_names[name]
         h, w, c, fp32 = self.plan.bufs[i]
-        arr = np.empty(self.B * h * w * c, dtype=np.float32 if fp32 else np.uint16)
+        nb = 1 if i in self.plan.stack_bufs else self.B
+        arr = np.empty(nb * h * w * c, dtype=np.float32 if fp32 else np.uint16)
         _lib.check(_lib.lib().vgh_detector_read_buffer(self._h, i, arr.ctypes.data, arr.nbytes), "read_buffer")
         t = torch.from_numpy(arr) if fp32 else torch.from_numpy(arr.view(np.int16)).view(torch.bfloat16).float()
-        return t.reshape(self.B, h, w, c)
+        return t.reshape(nb, h, w, c)
 
     def autotune(self, iters=3):
         _lib.check(_lib.lib().vgh_detector_autotune(self._h, iters, _lib.stream_ptr()), "autotune")
@@ -204,7 +216,7 @@ class Engine:
         rows = []
         for op, t in zip(self.plan.ops, ms):
             flops = 0
-            if op.kind == _lib.OP_CONV:
+            if op.kind == _lib.OP_CONV and not op.level:   # patch-level convs: work depends on the survivors, not counted
                 src_res = self.plan.bufs[op.src[0]][0]
                 out_res = src_res if op.up else src_res // op.stride
                 for p in op.parts:

@@ -89,11 +89,16 @@ int vgh_letterbox(const uint8_t* src_dev, const int64_t* offsets, const int32_t*
 typedef struct {
   int32_t H, W, C;   /* spatial size and channels per pixel */
   int32_t fp32;      /* 0 = bf16, 1 = fp32 (raw head outputs) */
+  int32_t stack;     /* 0 = batched [B,H,W,C]; 1 = ONE stacked image [H,W,C] (survivor patches, sparse heads) */
 } vgh_buf_desc;
 
 /* VGH_OP_STEM: im2col of the uint8 image for the 3x3 stride-2 stem -> bf16 [B,S/2,S/2,32] (27 taps in
- * (ky,kx,c) order + 5 zeros); the stem itself is then a VGH_OP_CONV with cin = 32. */
-enum { VGH_OP_STEM = 0, VGH_OP_CONV = 1, VGH_OP_SPP = 2 };
+ * (ky,kx,c) order + 5 zeros); the stem itself is then a VGH_OP_CONV with cin = 32.
+ * Sparse heads (n_dense_ops < n_ops): the FLAME branch of a head level is only read at the anchors that survive
+ * NMS and its receptive field there is 7x7 pixels, so its ops run AFTER select/NMS on 8x8 windows gathered around
+ * the survivors (VGH_OP_PATCH_GATHER), stacked as one tall image per level; VGH_OP_PATCH_MASK zeroes the window
+ * pixels outside the feature map (the dense graph's conv padding).  Such ops carry level = 1 + head level. */
+enum { VGH_OP_STEM = 0, VGH_OP_CONV = 1, VGH_OP_SPP = 2, VGH_OP_PATCH_GATHER = 3, VGH_OP_PATCH_MASK = 4 };
 
 typedef struct {
   int32_t kind;
@@ -106,7 +111,7 @@ typedef struct {
   float res_alpha;
   int32_t n_pad, k_total, block_n;   /* packed weight matrix [n_pad][k_total] bf16, UMMA N */
   int64_t w_off, b_off;              /* element offsets into the weight / bias blobs */
-  int32_t lane, reserved;            /* independent graph branches run on separate lanes (streams); 0 = main */
+  int32_t lane, level;               /* independent graph branches run on separate lanes (streams), 0 = main; level: see above */
 } vgh_op_desc;
 
 typedef struct {
@@ -120,6 +125,8 @@ typedef struct {
   int64_t n_bias;
   int32_t reg_buf[3], flame_buf[3]; /* raw head output buffers per level (fp32) */
   int32_t keep_k;                /* capacity of survivors per image (keep_top_k, utils.py:166) */
+  int32_t n_dense_ops;           /* ops [0, n_dense_ops) run before select/NMS, the rest after it on survivor patches;
+                                    0 or n_ops = single-phase (dense) plan */
 } vgh_net_desc;
 
 int vgh_detector_create(const vgh_net_desc* net, const vgh_flame* flame, vgh_detector** out);

@@ -14,10 +14,26 @@ def bf16_round(t):
     return t.to(torch.bfloat16).to(torch.float32)
 
 
-def apply_op(pk, op, m, bufs, images_u8=None, emulate_bf16=True):
-    """Execute ONE plan op on the given NHWC float buffers (in place)."""
+def apply_op(pk, op, m, bufs, images_u8=None, emulate_bf16=True, patches=None):
+    """Execute ONE plan op on the given NHWC float buffers (in place).  `patches[level]` = list of (image, y, x)
+    survivor anchors of head level `level` (1-based) for the sparse-heads ops."""
     P = pk.plan
     rnd = bf16_round if emulate_bf16 else (lambda t: t)
+    if op.kind in (_lib.OP_PATCH_GATHER, _lib.OP_PATCH_MASK):
+        PT, PC = arch.PATCH, arch.PATCH_C
+        sb, so, C = op.src
+        db, do = op.dst
+        for pi, (b, y, x) in enumerate(patches[op.level]):
+            feat_h, feat_w = (bufs[sb].shape[1], bufs[sb].shape[2]) if op.kind == _lib.OP_PATCH_GATHER else P.bufs[P.reg_buf[op.level - 1]][:2]
+            for r in range(PT):
+                for c in range(PT):
+                    yy, xx = y - PC + r, x - PC + c
+                    inside = 0 <= yy < feat_h and 0 <= xx < feat_w
+                    if op.kind == _lib.OP_PATCH_GATHER:
+                        bufs[db][0, pi * PT + r, c, do:do + C] = bufs[sb][b, yy, xx, so:so + C] if inside else 0.0
+                    elif not inside:
+                        bufs[db][0, pi * PT + r, c, do:do + C] = 0.0
+        return
     if op.kind == _lib.OP_STEM:  # im2col of the uint8 image: [B,S/2,S/2,32] = 27 taps (ky,kx,c) + 5 zeros
         x = images_u8.permute(0, 3, 1, 2).float()
         cols = F.unfold(x, kernel_size=3, padding=1, stride=2)            # [B, c*9 + ky*3 + kx, L]
@@ -56,12 +72,15 @@ def apply_op(pk, op, m, bufs, images_u8=None, emulate_bf16=True):
             bufs[db][..., do:do + op.cout] = y
 
 
-def run_plan(pk: arch.PackedNet, images_u8: torch.Tensor, emulate_bf16: bool = True):
-    """images_u8 [B,S,S,3] uint8 -> list of NHWC float buffers."""
+def run_plan(pk: arch.PackedNet, images_u8: torch.Tensor, emulate_bf16: bool = True, patches=None):
+    """images_u8 [B,S,S,3] uint8 -> list of NHWC float buffers.  Two-phase (sparse heads) plans run their dense ops
+    only unless `patches` = {level: [(image, y, x), ...]} names the survivor anchors the patch ops work on."""
     B = images_u8.shape[0]
-    bufs = [torch.zeros(B, h, w, c) for (h, w, c, _) in pk.plan.bufs]
-    for op, m in zip(pk.plan.ops, pk.op_meta):
-        apply_op(pk, op, m, bufs, images_u8, emulate_bf16)
+    P = pk.plan
+    bufs = [torch.zeros(1 if i in P.stack_bufs else B, h, w, c) for i, (h, w, c, _) in enumerate(P.bufs)]
+    n_ops = len(P.ops) if (patches is not None or P.n_dense_ops is None) else P.n_dense_ops
+    for op, m in list(zip(P.ops, pk.op_meta))[:n_ops]:
+        apply_op(pk, op, m, bufs, images_u8, emulate_bf16, patches)
     return bufs
 
 

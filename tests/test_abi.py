@@ -27,7 +27,7 @@ def test_version_and_error_string():
 
 
 def test_struct_sizes_match_c_layout():
-    assert ctypes.sizeof(_lib.BufDesc) == 16
+    assert ctypes.sizeof(_lib.BufDesc) == 20
     assert ctypes.sizeof(_lib.OpDesc) == 18 * 4 + 2 * 8 + 2 * 4
     assert ctypes.sizeof(_lib.NetDesc) % 8 == 0
 

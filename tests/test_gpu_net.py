@@ -387,3 +387,56 @@ def test_autotuned_configuration_keeps_parity():
         assert err.mean().item() <= 4e-3 * scale, (name, err.mean().item(), scale)
         drift = (got - before[name]).abs()
         assert drift.max().item() <= 2 ** -5 * scale + 1e-4 and drift.mean().item() <= 4e-3 * scale, (name, drift.max().item())
+
+
+def _border_and_cluster_heads(B, A, S, seed):
+    """Engineered detections (clusters of overlapping boxes) plus isolated high-score anchors in the corners / on
+    the edges of every head level, so that survivor patches hang over the image border."""
+    from head_detector_b200 import synth
+
+    boxes, scores = synth.engineered_heads(B, A, S, heads=5, per_cluster=8, seed=seed)
+    a_off, extra = 0, []
+    for stride in (8, 16, 32):
+        W = S // stride
+        for (y, x) in ((0, 0), (0, W - 1), (W - 1, 0), (W - 1, W - 1), (0, W // 2), (W // 2, W - 1), (1, 1)):
+            extra.append((a_off + y * W + x, (x + 0.5) * stride, (y + 0.5) * stride, stride))
+        a_off += W * W
+    for k, (a, cx, cy, stride) in enumerate(extra):
+        b = k % B
+        boxes[b, a] = torch.tensor([cx - 1.5, cy - 1.5, cx + 1.5, cy + 1.5])     # 3 px boxes: no overlap with anything
+        scores[b, a] = 0.97 - 1e-3 * k
+    return boxes, scores
+
+
+@pytest.mark.parametrize("S,B", [(128, 3), (640, 2)])
+def test_sparse_heads_match_dense_heads(S, B):
+    """FLAME branch on survivor patches (after NMS) vs on the whole maps: same survivors, same 413-float rows,
+    same vertices - including survivors in the corners / on the borders of every level (patch masks)."""
+    from head_detector_b200 import synth
+    from head_detector_b200.engine import Engine
+
+    w = no.synthetic_weights(8)
+    dense, sparse = Engine(w, B, S, sparse_heads=False), Engine(w, B, S, sparse_heads=True)
+    assert sparse.launch_count == 0 and len(sparse.plan.ops) > len(dense.plan.ops)
+    img = synth.synthetic_images(B, S, seed=21).cuda()
+    boxes, scores = _border_and_cluster_heads(B, dense.A, S, seed=5)
+    out = []
+    for eng in (dense, sparse):
+        eng.set_override(boxes.cuda(), scores.cuda())
+        eng.forward(img)
+        eng.postprocess(0.5, 0.5, 1000)
+        torch.cuda.synchronize()
+        n = int(eng.head_offsets[-1])
+        out.append((n, eng.keep_idx.cpu(), eng.head_params(n).cpu(), eng.head_verts(n).cpu()))
+    (n0, idx0, p0, v0), (n1, idx1, p1, v1) = out
+    assert n0 == n1 >= 21 + B and torch.equal(idx0, idx1)
+    scale = p0.abs().amax(dim=0).clamp_min(1.0)
+    assert ((p0 - p1).abs() / scale).max().item() < 1e-5, ((p0 - p1).abs() / scale).max().item()
+    assert (v0 - v1).abs().max().item() < 1e-3 * max(1.0, v0.abs().max().item() / 640)
+    # the graph path replays the same two-phase pipeline
+    sparse.input.copy_(img)
+    sparse.run_device(0.5, 0.5, 1000)
+    torch.cuda.synchronize()
+    assert int(sparse.head_offsets[-1]) == n1 and torch.equal(sparse.head_params(n1).cpu(), p1)
+    with pytest.raises(RuntimeError):
+        sparse.dense_flame()

@@ -111,3 +111,31 @@ def test_product_fold_matches_oracle_fold_and_unfused_forward():
     import pytest
     with pytest.raises(ValueError):
         arch.deploy_from_unfused(bad)
+
+
+def test_sparse_heads_plan_equals_dense_plan_at_survivors():
+    """Two-phase plan (FLAME branch on 8x8 survivor patches after NMS) against the dense plan, both interpreted
+    on the CPU: identical raw FLAME rows at the survivors - interior anchors, anchors on the image border / in
+    the corners (the patch mask reproduces the dense graph's zero padding layer by layer) and vertically stacked
+    neighbours - and an untouched box branch."""
+    import plan_emulator as pe
+    from head_detector_b200 import arch
+
+    S, B, K = 128, 2, 6
+    w = no.synthetic_weights(3)
+    dense = arch.pack(arch.build_plan(S), w)
+    sparse = arch.pack(arch.build_plan(S, sparse_heads=(B, K)), w)
+    assert sparse.plan.n_dense_ops is not None and all(op.level > 0 for op in sparse.plan.ops[sparse.plan.n_dense_ops:])
+    assert all(op.level == 0 for op in sparse.plan.ops[:sparse.plan.n_dense_ops])
+    torch.manual_seed(0)
+    img = torch.randint(0, 256, (B, S, S, 3), dtype=torch.uint8)
+    patches = {1: [(0, 0, 0), (1, 15, 7), (0, 8, 8), (1, 3, 15), (0, 15, 15)], 2: [(0, 0, 3), (1, 7, 7), (1, 4, 4)], 3: [(1, 0, 0), (0, 3, 2), (0, 1, 3)]}
+    with torch.no_grad():
+        ref = pe.run_plan(dense, img, emulate_bf16=True)
+        got = pe.run_plan(sparse, img, emulate_bf16=True, patches=patches)
+    for l in (1, 2, 3):
+        assert torch.equal(ref[dense.plan.reg_buf[l - 1]], got[sparse.plan.reg_buf[l - 1]])
+        fd, fs = ref[dense.plan.flame_buf[l - 1]], got[sparse.plan.flame_buf[l - 1]]
+        for pi, (b, y, x) in enumerate(patches[l]):
+            want, have = fd[b, y, x], fs[0, pi * arch.PATCH + arch.PATCH_C, arch.PATCH_C]
+            assert (want - have).abs().max().item() <= 1e-5 * max(1.0, want.abs().max().item()), (l, b, y, x)

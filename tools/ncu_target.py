@@ -12,7 +12,7 @@ from head_detector_b200.engine import Engine  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 tune = len(sys.argv) > 2 and sys.argv[2] == "tuned"
-eng = Engine(arch.synthetic_weights(0), B, 640)
+eng = Engine(arch.synthetic_weights(0), B, 640)  # VGGHEADS_B200_SPARSE_HEADS=1 selects the two-phase (sparse heads) plan
 img = synth.synthetic_images(B, 640, 0).cuda()
 boxes, scores = synth.engineered_heads(B, eng.A, 640, 8, seed=7)
 eng.set_override(boxes.cuda(), scores.cuda())
