@@ -43,12 +43,12 @@ def _peaks():
     return {"tflops": 1400.0, "hbm": 6650.0, "src": "fallback (B200_PROFILING.md)"}
 
 
-def ncu_conv_traffic():
+def ncu_conv_traffic(dense_heads=False):
     """DRAM bytes moved by the conv_igemm launches of ONE step (dram__bytes_read+write summed over the
     launches) from the committed ncu launch list of the same workload; None if the file is absent."""
     import csv
 
-    path = os.path.join(ROOT, "profiles", "r1_xr_ncu_launches_metrics.csv")
+    path = os.path.join(ROOT, "profiles", "r1_xr_ncu_launches_metrics.csv" if dense_heads else "r1_sparse_ncu_launches.csv")
     if not os.path.exists(path):
         return None
     tot = 0.0
@@ -358,8 +358,8 @@ def run_ours(args, rank, world, local_rank):
                 "flops_note": "EXECUTED conv FLOPs of the dense launches / their summed durations" + ("" if args.dense_heads else
                               f"; the reference graph's {dense_flops / 1e12:.2f} TFLOP/step include {100 * (1 - conv_flops / dense_flops):.0f} % "
                               "of FLAME-branch work at anchors NMS discards, which this build does not execute (and does not count)"),
-                "frac": ach / pk["tflops"], "peak_source": pk["src"], "traffic": ncu_conv_traffic(),
-                "traffic_note": "DRAM bytes of all conv_igemm launches of one step (profiles/r1_xr_ncu_launches_metrics.csv); algorithmic activation bytes are ~13 GB/step",
+                "frac": ach / pk["tflops"], "peak_source": pk["src"], "traffic": ncu_conv_traffic(args.dense_heads),
+                "traffic_note": "DRAM bytes of all conv_igemm launches of one step (ncu launch list of the same step under profiles/: r1_sparse_ncu_launches.csv, or r1_xr_ncu_launches_metrics.csv with --dense-heads); algorithmic activation bytes are ~13 GB/step",
                 "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_ms / all_ms,
                 "algorithmic_flops_per_step": conv_flops}
         if world == 1:

@@ -300,29 +300,55 @@ int flame_gather_launch(const DecodeLevels& lv, const int* keep_idx, const int* 
 }
 
 // ---------------------------------------------------------------------------------------- sparse heads
-// One warp walks the survivors image by image, slot by slot (the packed head order) and hands out patch numbers
-// per level with ballot prefix counts: deterministic, image-major patch order on every level.
-__global__ void __launch_bounds__(32) patch_assign_kernel(const DecodeLevels lv, const int* __restrict__ keep_idx,
-                                                          const int* __restrict__ keep_cnt, const int* __restrict__ offsets, int B,
-                                                          int keep_k, int cap, int* __restrict__ head_level,
-                                                          int* __restrict__ head_patch, int* __restrict__ patch_src,
-                                                          int* __restrict__ level_rows) {
-  const int lane = threadIdx.x;
-  int run[3] = {0, 0, 0};
-  for (int b = 0; b < B; ++b) {
+// Patch numbers per level in image-major, slot-major order (deterministic): pass 1 counts the survivors of every
+// (image, level) - one warp per image -, an exclusive scan over the images gives each image's first patch number
+// per level, pass 2 hands the numbers out with ballot prefix counts.
+__global__ void __launch_bounds__(1024) patch_assign_kernel(const DecodeLevels lv, const int* __restrict__ keep_idx,
+                                                            const int* __restrict__ keep_cnt, const int* __restrict__ offsets, int B,
+                                                            int keep_k, int cap, int* __restrict__ head_level,
+                                                            int* __restrict__ head_patch, int* __restrict__ patch_src,
+                                                            int* __restrict__ level_rows) {
+  extern __shared__ int base_s[];  // [3][B] counts, then exclusive prefixes
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  auto level_of = [&](int a, int& y, int& x) {
+    int l = 0;
+    while (l < 2 && a >= lv.a_off[l + 1]) ++l;
+    const int pix = a - lv.a_off[l];
+    y = pix / lv.W[l];
+    x = pix - y * lv.W[l];
+    return l;
+  };
+  for (int b = warp; b < B; b += n_warps) {
     const int n = min(keep_cnt[b], keep_k);
+    int c[3] = {0, 0, 0};
     for (int base = 0; base < n; base += 32) {
       const int j = base + lane;
-      const bool valid = j < n;
+      int l = -1, y, x;
+      if (j < n) l = level_of(keep_idx[b * keep_k + j], y, x);
+#pragma unroll
+      for (int q = 0; q < 3; ++q) c[q] += __popc(__ballot_sync(0xffffffffu, l == q));
+    }
+    if (lane < 3) base_s[lane * B + b] = c[lane];
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {  // exclusive scan over the images (B is a batch size: tens to hundreds)
+    int run = 0;
+    int* row = base_s + threadIdx.x * B;
+    for (int b = 0; b < B; ++b) {
+      const int v = row[b];
+      row[b] = run;
+      run += v;
+    }
+    level_rows[threadIdx.x] = min(run, cap) * kPatch;
+  }
+  __syncthreads();
+  for (int b = warp; b < B; b += n_warps) {
+    const int n = min(keep_cnt[b], keep_k);
+    int run[3] = {base_s[b], base_s[B + b], base_s[2 * B + b]};
+    for (int base = 0; base < n; base += 32) {
+      const int j = base + lane;
       int l = -1, y = 0, x = 0;
-      if (valid) {
-        const int a = keep_idx[b * keep_k + j];
-        l = 0;
-        while (l < 2 && a >= lv.a_off[l + 1]) ++l;
-        const int pix = a - lv.a_off[l];
-        y = pix / lv.W[l];
-        x = pix - y * lv.W[l];
-      }
+      if (j < n) l = level_of(keep_idx[b * keep_k + j], y, x);
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
         const unsigned m = __ballot_sync(0xffffffffu, l == q);
@@ -338,12 +364,13 @@ __global__ void __launch_bounds__(32) patch_assign_kernel(const DecodeLevels lv,
       }
     }
   }
-  if (lane < 3) level_rows[lane] = min(run[lane], cap) * kPatch;
 }
 
 int patch_assign_launch(const DecodeLevels& lv, const int* keep_idx, const int* keep_cnt, const int* offsets, int B, int keep_k,
                         int cap, int* head_level, int* head_patch, int* patch_src, int* level_rows, cudaStream_t stream) {
-  patch_assign_kernel<<<1, 32, 0, stream>>>(lv, keep_idx, keep_cnt, offsets, B, keep_k, cap, head_level, head_patch, patch_src, level_rows);
+  if (B > 4096) return 1;
+  patch_assign_kernel<<<1, 1024, 3 * B * sizeof(int), stream>>>(lv, keep_idx, keep_cnt, offsets, B, keep_k, cap, head_level, head_patch,
+                                                                patch_src, level_rows);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
@@ -351,50 +378,52 @@ int patch_assign_launch(const DecodeLevels& lv, const int* keep_idx, const int* 
 __global__ void __launch_bounds__(256) patch_gather_kernel(const __nv_bfloat16* __restrict__ feat, int H, int W, int C_total, int coff,
                                                            int C, __nv_bfloat16* __restrict__ dst, int dst_C, int dst_coff,
                                                            const int* __restrict__ patch_src, const int* __restrict__ level_rows) {
-  const int p = blockIdx.x;
-  if (p * kPatch >= *level_rows) return;
-  const int src = patch_src[p];
-  const int b = src >> 20, y0 = ((src >> 10) & 1023) - kPatchC, x0 = (src & 1023) - kPatchC;
+  const int n_patches = *level_rows / kPatch;
   const int vec = C >> 3;  // uint4 = 8 bf16
-  for (int i = threadIdx.x; i < kPatch * kPatch * vec; i += blockDim.x) {
-    const int pix = i / vec, v = i - pix * vec;
-    const int r = pix / kPatch, c = pix - r * kPatch;
-    const int yy = y0 + r, xx = x0 + c;
-    uint4 val = make_uint4(0, 0, 0, 0);
-    if (yy >= 0 && yy < H && xx >= 0 && xx < W)
-      val = __ldg(reinterpret_cast<const uint4*>(feat + ((static_cast<size_t>(b) * H + yy) * W + xx) * C_total + coff) + v);
-    reinterpret_cast<uint4*>(dst + (static_cast<size_t>(p) * kPatch * kPatch + pix) * dst_C + dst_coff)[v] = val;
+  for (int p = blockIdx.x; p < n_patches; p += gridDim.x) {  // grid = a few CTAs per SM, not the patch capacity
+    const int src = patch_src[p];
+    const int b = src >> 20, y0 = ((src >> 10) & 1023) - kPatchC, x0 = (src & 1023) - kPatchC;
+    for (int i = threadIdx.x; i < kPatch * kPatch * vec; i += blockDim.x) {
+      const int pix = i / vec, v = i - pix * vec;
+      const int r = pix / kPatch, c = pix - r * kPatch;
+      const int yy = y0 + r, xx = x0 + c;
+      uint4 val = make_uint4(0, 0, 0, 0);
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+        val = __ldg(reinterpret_cast<const uint4*>(feat + ((static_cast<size_t>(b) * H + yy) * W + xx) * C_total + coff) + v);
+      reinterpret_cast<uint4*>(dst + (static_cast<size_t>(p) * kPatch * kPatch + pix) * dst_C + dst_coff)[v] = val;
+    }
   }
 }
 
 int patch_gather_launch(const __nv_bfloat16* feat, int H, int W, int C_total, int coff, int C, __nv_bfloat16* dst, int dst_C,
                         int dst_coff, const int* patch_src, const int* level_rows, int cap, cudaStream_t stream) {
   if (C % 8 || C_total % 8 || coff % 8 || dst_C % 8 || dst_coff % 8) return 1;
-  patch_gather_kernel<<<cap, 256, 0, stream>>>(feat, H, W, C_total, coff, C, dst, dst_C, dst_coff, patch_src, level_rows);
+  patch_gather_kernel<<<cap < 592 ? cap : 592, 256, 0, stream>>>(feat, H, W, C_total, coff, C, dst, dst_C, dst_coff, patch_src, level_rows);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
 __global__ void __launch_bounds__(128) patch_mask_kernel(__nv_bfloat16* __restrict__ buf, int C_total, int coff, int C, int H, int W,
                                                          const int* __restrict__ patch_src, const int* __restrict__ level_rows) {
-  const int p = blockIdx.x;
-  if (p * kPatch >= *level_rows) return;
-  const int src = patch_src[p];
-  const int y0 = ((src >> 10) & 1023) - kPatchC, x0 = (src & 1023) - kPatchC;
-  if (y0 >= 0 && x0 >= 0 && y0 + kPatch <= H && x0 + kPatch <= W) return;  // interior patch: nothing lies outside
+  const int n_patches = *level_rows / kPatch;
   const int vec = C >> 3;
-  for (int i = threadIdx.x; i < kPatch * kPatch * vec; i += blockDim.x) {
-    const int pix = i / vec, v = i - pix * vec;
-    const int r = pix / kPatch, c = pix - r * kPatch;
-    const int yy = y0 + r, xx = x0 + c;
-    if (yy >= 0 && yy < H && xx >= 0 && xx < W) continue;
-    reinterpret_cast<uint4*>(buf + (static_cast<size_t>(p) * kPatch * kPatch + pix) * C_total + coff)[v] = make_uint4(0, 0, 0, 0);
+  for (int p = blockIdx.x; p < n_patches; p += gridDim.x) {
+    const int src = patch_src[p];
+    const int y0 = ((src >> 10) & 1023) - kPatchC, x0 = (src & 1023) - kPatchC;
+    if (y0 >= 0 && x0 >= 0 && y0 + kPatch <= H && x0 + kPatch <= W) continue;  // interior patch: nothing lies outside
+    for (int i = threadIdx.x; i < kPatch * kPatch * vec; i += blockDim.x) {
+      const int pix = i / vec, v = i - pix * vec;
+      const int r = pix / kPatch, c = pix - r * kPatch;
+      const int yy = y0 + r, xx = x0 + c;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) continue;
+      reinterpret_cast<uint4*>(buf + (static_cast<size_t>(p) * kPatch * kPatch + pix) * C_total + coff)[v] = make_uint4(0, 0, 0, 0);
+    }
   }
 }
 
 int patch_mask_launch(__nv_bfloat16* buf, int C_total, int coff, int C, int H, int W, const int* patch_src,
                       const int* level_rows, int cap, cudaStream_t stream) {
   if (C % 8 || C_total % 8 || coff % 8) return 1;
-  patch_mask_kernel<<<cap, 128, 0, stream>>>(buf, C_total, coff, C, H, W, patch_src, level_rows);
+  patch_mask_kernel<<<cap < 296 ? cap : 296, 128, 0, stream>>>(buf, C_total, coff, C, H, W, patch_src, level_rows);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
