@@ -389,12 +389,12 @@ def test_autotuned_configuration_keeps_parity():
         assert drift.max().item() <= 2 ** -5 * scale + 1e-4 and drift.mean().item() <= 4e-3 * scale, (name, drift.max().item())
 
 
-def _border_and_cluster_heads(B, A, S, seed):
+def _border_and_cluster_heads(B, A, S, seed, heads=5):
     """Engineered detections (clusters of overlapping boxes) plus isolated high-score anchors in the corners / on
     the edges of every head level, so that survivor patches hang over the image border."""
     from head_detector_b200 import synth
 
-    boxes, scores = synth.engineered_heads(B, A, S, heads=5, per_cluster=8, seed=seed)
+    boxes, scores = synth.engineered_heads(B, A, S, heads=heads, per_cluster=8, seed=seed)
     a_off, extra = 0, []
     for stride in (8, 16, 32):
         W = S // stride
@@ -408,8 +408,8 @@ def _border_and_cluster_heads(B, A, S, seed):
     return boxes, scores
 
 
-@pytest.mark.parametrize("S,B", [(128, 3), (640, 2)])
-def test_sparse_heads_match_dense_heads(S, B):
+@pytest.mark.parametrize("S,B,heads", [(128, 3, 5), (640, 2, 5), (1280, 1, 30)])
+def test_sparse_heads_match_dense_heads(S, B, heads):
     """FLAME branch on survivor patches (after NMS) vs on the whole maps: same survivors, same 413-float rows,
     same vertices - including survivors in the corners / on the borders of every level (patch masks)."""
     from head_detector_b200 import synth
@@ -419,7 +419,7 @@ def test_sparse_heads_match_dense_heads(S, B):
     dense, sparse = Engine(w, B, S, sparse_heads=False), Engine(w, B, S, sparse_heads=True)
     assert sparse.launch_count == 0 and len(sparse.plan.ops) > len(dense.plan.ops)
     img = synth.synthetic_images(B, S, seed=21).cuda()
-    boxes, scores = _border_and_cluster_heads(B, dense.A, S, seed=5)
+    boxes, scores = _border_and_cluster_heads(B, dense.A, S, seed=5, heads=heads)
     out = []
     for eng in (dense, sparse):
         eng.set_override(boxes.cuda(), scores.cuda())
@@ -429,7 +429,7 @@ def test_sparse_heads_match_dense_heads(S, B):
         n = int(eng.head_offsets[-1])
         out.append((n, eng.keep_idx.cpu(), eng.head_params(n).cpu(), eng.head_verts(n).cpu()))
     (n0, idx0, p0, v0), (n1, idx1, p1, v1) = out
-    assert n0 == n1 >= 21 + B and torch.equal(idx0, idx1)
+    assert n0 == n1 >= 21 + min(B * heads, 20) // 2 and torch.equal(idx0, idx1)
     scale = p0.abs().amax(dim=0).clamp_min(1.0)
     assert ((p0 - p1).abs() / scale).max().item() < 1e-5, ((p0 - p1).abs() / scale).max().item()
     assert (v0 - v1).abs().max().item() < 1e-3 * max(1.0, v0.abs().max().item() / 640)
@@ -440,3 +440,10 @@ def test_sparse_heads_match_dense_heads(S, B):
     assert int(sparse.head_offsets[-1]) == n1 and torch.equal(sparse.head_params(n1).cpu(), p1)
     with pytest.raises(RuntimeError):
         sparse.dense_flame()
+    # no survivor at all: every patch-phase launch is empty
+    sparse.run_device(0.9999, 0.5, 1000)
+    torch.cuda.synchronize()
+    assert int(sparse.head_offsets[-1]) == 0 and int(sparse.keep_cnt.sum()) == 0
+    sparse.run_device(0.5, 0.5, 1000)
+    torch.cuda.synchronize()
+    assert int(sparse.head_offsets[-1]) == n1 and torch.equal(sparse.head_params(n1).cpu(), p1)
