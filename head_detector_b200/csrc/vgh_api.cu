@@ -717,12 +717,6 @@ extern "C" int vgh_detector_autotune(vgh_detector* d, int iters, void* stream) {
       for (int max_px : {256, 192, 128}) for (int cl = 0; cl <= cluster_default(); ++cl) {  // pixel-tile size trades MMA width against pipeline depth
         OpRt t = o;
         t.cfg_ks = 1; t.cfg_xr = 0; t.cfg_cluster = cl;
-        if (max_px > 1000) {  // same tile sizes with several k-blocks per barrier round (shallow BK=32 blocks)
-          max_px -= 1000;
-          const int cblks = o.d.cin / o.bk;
-          t.cfg_ks = (cblks % 3 == 0) ? 3 : ((cblks % 2 == 0) ? 2 : 1);
-          if (t.cfg_ks == 1) continue;
-        }
         t.cfg_swap = 1; t.cfg_mt = 0; t.cfg_stages = 0;
         pick_tile_swap(o.L.Ho, o.L.Wo, t.cfg_tw, t.cfg_th, max_px);
         if (max_px != 256 && t.cfg_tw * t.cfg_th > max_px) continue;
