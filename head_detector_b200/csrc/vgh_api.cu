@@ -554,10 +554,12 @@ static int run_ops(vgh_detector* d, int op_begin, int op_end, const uint8_t* ima
   std::vector<int> last_w(static_cast<size_t>(n_bufs) * L, -1), last_r(static_cast<size_t>(n_bufs) * L, -1);
   std::vector<char> recorded(n_ops, 0);
   std::vector<int> last_op_on_lane(L, -1);
-  if (L > 1 && op_begin > 0) {  // later phase: whatever lane 0 has queued so far (select/NMS, patch tables) precedes every lane
+  // later phase: whatever lane 0 has queued so far (select/NMS, patch tables) precedes every lane; a side lane joins
+  // when its first op of the phase is issued (lanes without ops in this phase stay out of the capture)
+  std::vector<char> lane_joined(L, 0);
+  if (L > 1 && op_begin > 0) {
     if (!d->phase_event) CUDA_OK(cudaEventCreateWithFlags(&d->phase_event, cudaEventDisableTiming));
     CUDA_OK(cudaEventRecord(d->phase_event, s));
-    for (int l2 = 1; l2 < L; ++l2) CUDA_OK(cudaStreamWaitEvent(stream_of(l2), d->phase_event, 0));
   }
   auto depend = [&](int lane, int op_j) -> int {  // lane must wait for op_j (which ran on another lane)
     if (op_j < 0) return 0;
@@ -573,6 +575,10 @@ static int run_ops(vgh_detector* d, int op_begin, int op_end, const uint8_t* ima
   for (int i = op_begin; i < op_end; ++i) {
     OpRt& o = d->ops[i];
     const int lane = d->multi_lane ? o.d.lane : 0;
+    if (lane > 0 && op_begin > 0 && !lane_joined[lane]) {
+      CUDA_OK(cudaStreamWaitEvent(stream_of(lane), d->phase_event, 0));
+      lane_joined[lane] = 1;
+    }
     if (L > 1) {
       int reads[2] = {o.d.kind == VGH_OP_STEM ? -1 : o.d.in_buf, o.d.kind == VGH_OP_CONV ? o.d.res_buf : -1};
       for (int b : reads) {
