@@ -114,3 +114,23 @@ def test_empty_extent_is_an_error(harness):
     assert rc != 0
     with pytest.raises(ValueError):
         lo.transform_image(img)
+
+
+def test_random_shapes_oracle_and_kernel_arithmetic_vs_cv2(harness):
+    """Seeded sweep over odd shapes (up- and down-scaling, extreme aspect ratios, tiny images) and two letterbox
+    sizes: numpy oracle == cv2 == the product's device arithmetic run on the host."""
+    rng = np.random.default_rng(2024)
+    for _ in range(12):
+        h, w = int(rng.integers(1, 900)), int(rng.integers(1, 900))
+        S = int(rng.choice([96, 320]))
+        new_h, new_w = (S, int(w * S / h)) if h > w else (int(h * S / w), S)
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        if new_h <= 0 or new_w <= 0:
+            rc, _, _ = _harness_letterbox(harness, img, S)
+            assert rc != 0
+            continue
+        want, pad, scale = _cv2_letterbox(img, S)
+        got, gpad, gscale = lo.transform_image(img, S)
+        assert gpad == pad and gscale == scale and np.array_equal(got, want), (h, w, S)
+        rc, dev, geom = _harness_letterbox(harness, img, S)
+        assert rc == 0 and (geom[2], geom[3]) == pad and np.array_equal(dev, want), (h, w, S)
