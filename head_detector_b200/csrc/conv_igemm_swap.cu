@@ -24,18 +24,18 @@
 // row taps dy = 0,1,2 are three MMAs whose pixel-operand descriptor starts dy*tw rows further down
 // the same shared-memory tile.  With tw a multiple of 8 that offset is a whole number of 8-row swizzle
 // atoms, so the descriptors stay canonical.  3*(th+2) tile rows instead of 9*th: 2.4-2.7x less pixel
-// traffic.  Weights (identical for every CTA, coalesced in L2) keep streaming tap by tap through their
-// own, deeper ring; the pixel ring has 2-3 slots.  K order: (cin block, dx, dy).
+// traffic.  Weights keep streaming tap by tap through their own, deeper ring; the pixel ring has 2-3
+// slots.  K order: (cin block, dx, dy).
 //
-// Cluster variant (`p.cluster == 2`): the weight k-blocks are the same for every CTA but are not
-// coalesced in L2 - after the tap reuse they are more than half of the L2->SM bytes of a layer, and L2
-// bandwidth (8-9 TB/s of lts__t_bytes on every conv launch, profiles/r1_xr_ncu_launches_metrics.csv) is
-// what bounds the layers.  Two CTAs of a cluster work on two pixel tiles of the SAME channel group in
-// lock step; each fetches one half of every weight k-block and TMA-multicasts it into both CTAs' rings,
-// so the pair reads every weight byte from L2 once.  A slot is released to both producers by a multicast
-// tcgen05.commit from each consumer (empty barriers count 2).  Pixel tiles, TMEM, epilogue stay per CTA.
-// Measured neutral (the bound is per-SM ingest, which a multicast does not reduce) - off by default, kept as
-// the cluster plumbing (work-item mapping, cluster barriers, multicast commits) for cta_group::2 pairs.
+// Cluster variant (`p.cluster == 2`, off by default): after the tap reuse the weight k-blocks - the same
+// for every CTA - are more than half of the L2->SM bytes of a layer, and every conv launch plateaus at
+// 7-9 TB/s of lts__t_bytes (profiles/r1_xr_ncu_launches_metrics.csv).  Two CTAs of a cluster work on two
+// pixel tiles of the SAME channel group in lock step; each fetches one half of every weight k-block and
+// TMA-multicasts it into both CTAs' rings, so the pair reads every weight byte from L2 once.  A slot is
+// released to both producers by a multicast tcgen05.commit from each consumer (empty barriers count 2).
+// Pixel tiles, TMEM, epilogue stay per CTA.  Measured neutral (profiles/r1_xr_cluster_ab.txt): the bound
+// is the bytes each SM ingests, which a multicast does not reduce.  Kept, parity-tested, as the cluster
+// plumbing (work-item mapping per pair, cluster barriers, multicast commits) cta_group::2 MMA pairs need.
 //
 // Everything else matches conv_igemm.cu: persistent CTAs, TMA (4-D pixel box with OOB zero fill =
 // padding, traversal stride = conv stride; 2-D weight box), mbarrier ring, double-buffered TMEM.
