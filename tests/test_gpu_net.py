@@ -447,3 +447,28 @@ def test_sparse_heads_match_dense_heads(S, B, heads):
     sparse.run_device(0.5, 0.5, 1000)
     torch.cuda.synchronize()
     assert int(sparse.head_offsets[-1]) == n1 and torch.equal(sparse.head_params(n1).cpu(), p1)
+
+
+def test_full_batch_is_batch_composition_invariant():
+    """BASELINE batch (32 x 640 x 640), size-independent property: what the network computes for an image does not
+    depend on which batch it sits in or where - image k of the 32-batch equals the same image inside a 4-batch
+    (other tilings, other work-item packing, same arithmetic per pixel), and a repeated image gives repeated rows."""
+    from head_detector_b200 import synth
+    from head_detector_b200.engine import Engine
+
+    w = no.synthetic_weights(9)
+    big, small = Engine(w, 32, 640), Engine(w, 4, 640)
+    imgs = synth.synthetic_images(32, 640, seed=31)
+    imgs[9] = imgs[20]                                   # a repeated image inside the big batch
+    pick = [5, 17, 20, 31]
+    big.forward(imgs.cuda())
+    small.forward(imgs[pick].cuda())
+    torch.cuda.synchronize()
+    for name in ("c3", "c5", "p3", "p4", "p5", "head1.reg_raw", "head2.flame_raw", "head3.flame_raw"):
+        a, b = big.read_buffer(name), small.read_buffer(name)
+        scale = a.abs().max().item() + 1e-6
+        assert torch.equal(a[9], a[20]), name
+        err = (a[pick] - b).abs()
+        assert err.max().item() <= 2 ** -7 * scale and err.mean().item() <= 1e-4 * scale, (name, err.max().item(), err.mean().item(), scale)
+    assert torch.equal(big.boxes[9], big.boxes[20]) and torch.equal(big.scores[9], big.scores[20])
+    assert (big.boxes[pick] - small.boxes).abs().max().item() <= 0.05
