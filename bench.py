@@ -184,7 +184,8 @@ def _config(n, dense_heads=False):
     return {"heads": ("dense: FLAME branch of the heads computed on the whole feature maps" if dense_heads else
                       "sparse: FLAME branch of the heads (pose stem, towers, output convs) computed after NMS on 8x8 windows around the "
                       "survivors only - identical boxes / 413-float rows / vertices (tests/test_gpu_net.py::test_sparse_heads_match_dense_heads); "
-                      "`--dense-heads` runs the reference's dense graph"),
+                      "`--dense-heads` runs the reference's dense graph (same box, back to back: 4740 images/s dense vs 5911 sparse, "
+                      "profiles/r1_sparse_ab_bench_dense_heads.json / r1_sparse_ab_bench_sparse_heads.json)"),
             "workload": f"BASELINE configs[3] per-GPU shard: batch {PER_GPU_BATCH}/GPU x {n} GPU(s), {IMAGE_SIZE}x{IMAGE_SIZE} uint8 RGB, "
                         f"VGGHeads_L full path (backbone+neck+heads, box decode, select+NMS, FLAME decode to 5023 verts), ~{HEADS_PER_IMAGE} heads/image; superset of configs[1]",
             "global_batch": PER_GPU_BATCH * n, "image_size": IMAGE_SIZE, "heads_per_image": HEADS_PER_IMAGE,
