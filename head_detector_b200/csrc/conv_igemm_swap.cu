@@ -192,27 +192,27 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
               }
             }
           }
-          continue;
-        }
-        int tap = 0, cb = 0;
-        for (int kb = 0; kb < num_kb; kb += ks) {
-          mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-          const uint32_t fb = full_bar + 8 * stage;
-          mbar_arrive_expect_tx(fb, tx_bytes * ks);
-          for (int q = 0; q < ks; ++q) {
-            const int ty = tap / p.kw;
-            const int tx = tap - ty * p.kw;
-            tma_load_4d(x_base + (stage * ks + q) * x_slot, &p.tmA, fb, p.cin_off + cb * BK, w0 * p.stride + tx - p.pad,
-                        h0 * p.stride + ty - p.pad, b_img);
-            load_w(w_base + (stage * ks + q) * kWBytes, fb, tap * p.cin + cb * BK, n_base);
-            if (++cb == cblks) {
-              cb = 0;
-              ++tap;
+        } else {
+          int tap = 0, cb = 0;
+          for (int kb = 0; kb < num_kb; kb += ks) {
+            mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+            const uint32_t fb = full_bar + 8 * stage;
+            mbar_arrive_expect_tx(fb, tx_bytes * ks);
+            for (int q = 0; q < ks; ++q) {
+              const int ty = tap / p.kw;
+              const int tx = tap - ty * p.kw;
+              tma_load_4d(x_base + (stage * ks + q) * x_slot, &p.tmA, fb, p.cin_off + cb * BK, w0 * p.stride + tx - p.pad,
+                          h0 * p.stride + ty - p.pad, b_img);
+              load_w(w_base + (stage * ks + q) * kWBytes, fb, tap * p.cin + cb * BK, n_base);
+              if (++cb == cblks) {
+                cb = 0;
+                ++tap;
+              }
             }
-          }
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1;
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
         }
       }
@@ -257,27 +257,22 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
               xphase ^= 1;
             }
           }
-          umma_commit(tmem_full_bar + 8 * acc);
-          if (++acc == p.acc_stages) {
-            acc = 0;
-            acc_phase ^= 1;
-          }
-          continue;
-        }
-        for (int kb = 0; kb < num_kb; kb += ks) {
-          mbar_wait(full_bar + 8 * stage, phase);
-          tc_fence_after();
-          for (int q = 0; q < ks; ++q) {
-            const uint64_t w_desc = umma_smem_desc(w_base + (stage * ks + q) * kWBytes, kRowBytes);  // M side: weights
-            const uint64_t x_desc = umma_smem_desc(x_base + (stage * ks + q) * x_slot, kRowBytes);   // N side: pixels
+        } else {
+          for (int kb = 0; kb < num_kb; kb += ks) {
+            mbar_wait(full_bar + 8 * stage, phase);
+            tc_fence_after();
+            for (int q = 0; q < ks; ++q) {
+              const uint64_t w_desc = umma_smem_desc(w_base + (stage * ks + q) * kWBytes, kRowBytes);  // M side: weights
+              const uint64_t x_desc = umma_smem_desc(x_base + (stage * ks + q) * x_slot, kRowBytes);   // N side: pixels
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              umma_bf16(d, w_desc + 2 * k, x_desc + 2 * k, idesc, (kb | q | k) != 0 ? 1u : 0u);
-          }
-          if (n_cl > 1) umma_commit_mc(empty_bar + 8 * stage, mc_mask); else umma_commit(empty_bar + 8 * stage);
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1;
+              for (int k = 0; k < BK / 16; ++k)
+                umma_bf16(d, w_desc + 2 * k, x_desc + 2 * k, idesc, (kb | q | k) != 0 ? 1u : 0u);
+            }
+            if (n_cl > 1) umma_commit_mc(empty_bar + 8 * stage, mc_mask); else umma_commit(empty_bar + 8 * stage);
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
         }
         umma_commit(tmem_full_bar + 8 * acc);

@@ -18,8 +18,10 @@
 
 #if defined(__CUDACC__)
 #define VGH_HD __host__ __device__ __forceinline__
+#define VGH_UNROLL _Pragma("unroll")
 #else
 #define VGH_HD inline
+#define VGH_UNROLL
 #endif
 
 namespace vgh {
@@ -104,14 +106,14 @@ VGH_HD int lb_clamp(int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); }
 VGH_HD void lanczos4_pixel_rgb(const uint8_t* src, int h, int w, int x0, const int16_t* ax, int y0, const int16_t* ay,
                                uint8_t* out) {
   int xi[8];
-#pragma unroll
+VGH_UNROLL
   for (int k = 0; k < 8; ++k) xi[k] = lb_clamp(x0 + k, w - 1) * 3;
   int acc0 = 0, acc1 = 0, acc2 = 0;
-#pragma unroll
+VGH_UNROLL
   for (int ky = 0; ky < 8; ++ky) {
     const uint8_t* row = src + static_cast<int64_t>(lb_clamp(y0 + ky, h - 1)) * w * 3;
     int h0 = 0, h1 = 0, h2 = 0;
-#pragma unroll
+VGH_UNROLL
     for (int kx = 0; kx < 8; ++kx) {
       const uint8_t* p = row + xi[kx];
       const int a = ax[kx];
