@@ -345,6 +345,7 @@ def run_ours(args, rank, world, local_rank):
 
     # live roofline of the dominant kernel (conv_igemm): event pairs around every launch of one step
     roof = None
+    parity = None
     cpu_base = None
     if rank == 0:
         rows = eng.profile(iters=3, conf=CONF, iou=IOU, top_k=TOPK)
@@ -363,6 +364,24 @@ def run_ours(args, rank, world, local_rank):
                 "traffic_note": "DRAM bytes of all conv_igemm launches of one step (ncu launch list of the same step under profiles/: r1_sparse_ncu_launches.csv, or r1_xr_ncu_launches_metrics.csv with --dense-heads); algorithmic activation bytes are ~13 GB/step",
                 "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_ms / all_ms,
                 "algorithmic_flops_per_step": conv_flops}
+        # the other half of the BASELINE metric: parity of this very step against the oracle (checker only)
+        try:
+            from oracle import flame_oracle, nms_oracle
+
+            torch.cuda.synchronize()
+            off, cnt, idx = eng.head_offsets.cpu().numpy(), eng.keep_cnt.cpu().numpy(), eng.keep_idx.cpu().numpy()
+            n_chk = int(off[-1])
+            ids_ok = all(idx[b, :cnt[b]].tolist() == nms_oracle.select_nms(boxes[b].numpy(), scores[b].numpy(), CONF, IOU, TOPK, 100).tolist()
+                         for b in range(B))
+            err = 0.0
+            if n_chk:
+                p_chk, v_chk = eng.head_params(n_chk).cpu(), eng.head_verts(n_chk).cpu()
+                err = float((v_chk - flame_oracle.detector_vertices(p_chk, flame_oracle.load_flame_constants())).abs().max())
+            parity = {"vertices_3d_max_abs_err_px": err, "nms_ids_bit_exact": bool(ids_ok), "heads_checked": n_chk,
+                      "checker": "oracle/ on this step's own data: kept anchor ids vs the utils.nms restatement, vertices vs the FLAME "
+                                 "restatement applied to the device's 413-float rows (tolerance of the metric: 1e-4 px)"}
+        except Exception as ex:  # never lose the measurement line to the checker
+            parity = {"error": repr(ex)}
         if world == 1:
             import torch as _t
 
@@ -388,7 +407,7 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": imgs / e2e_s, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "mode": "vgh_detector_submit_host/collect_host over 2 detector handles (3 batches in flight)" + (" + NCCL gather of every step" if world > 1 else "")},
             "gpu_launches": eng.launch_count * args.steps,
-            "roofline": roof, "cpu_baseline": cpu_base,
+            "roofline": roof, "cpu_baseline": cpu_base, "parity": parity,
             "heads_per_step_per_gpu": heads_total,
             "conv_gflop_per_image": 2 * arch.total_macs(IMAGE_SIZE) / 1e9,
         }
