@@ -193,6 +193,31 @@ def _config(n, dense_heads=False):
             "weights": "seeded random-init, deploy (re-parameterised) form", "in_flight": "2 batches per GPU (two detector handles on two streams)", "l2": "per-step working set ~5 GB >> 126 MB L2; 4 rotating input batches (157 MB)"}
 
 
+def parity_check(eng, boxes, scores, batch):
+    """The other half of the BASELINE metric, on the step the engine has just run: kept anchor ids against the
+    utils.nms restatement (bit-exact) and vertices against the FLAME restatement applied to the device's own
+    413-float rows (bar: 1e-4 px).  oracle/ is the checker here, never the thing measured."""
+    try:
+        import torch
+
+        from oracle import flame_oracle, nms_oracle
+
+        torch.cuda.synchronize()
+        off, cnt, idx = eng.head_offsets.cpu().numpy(), eng.keep_cnt.cpu().numpy(), eng.keep_idx.cpu().numpy()
+        n_chk = int(off[-1])
+        ids_ok = all(idx[b, :cnt[b]].tolist() == nms_oracle.select_nms(boxes[b].numpy(), scores[b].numpy(), CONF, IOU, TOPK, 100).tolist()
+                     for b in range(batch))
+        err = 0.0
+        if n_chk:
+            p_chk, v_chk = eng.head_params(n_chk).cpu(), eng.head_verts(n_chk).cpu()
+            err = float((v_chk - flame_oracle.detector_vertices(p_chk, flame_oracle.load_flame_constants())).abs().max())
+        return {"vertices_3d_max_abs_err_px": err, "nms_ids_bit_exact": bool(ids_ok), "heads_checked": n_chk,
+                "checker": "oracle/ on this step's own data: kept anchor ids vs the utils.nms restatement, vertices vs the FLAME "
+                           "restatement applied to the device's 413-float rows (tolerance of the metric: 1e-4 px)"}
+    except Exception as ex:  # never lose the measurement line to the checker
+        return {"error": repr(ex)}
+
+
 # ------------------------------------------------------------------------------------------ GPU arm
 def run_ours(args, rank, world, local_rank):
     import torch
@@ -364,24 +389,7 @@ def run_ours(args, rank, world, local_rank):
                 "traffic_note": "DRAM bytes of all conv_igemm launches of one step (ncu launch list of the same step under profiles/: r1_sparse_ncu_launches.csv, or r1_xr_ncu_launches_metrics.csv with --dense-heads); algorithmic activation bytes are ~13 GB/step",
                 "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_ms / all_ms,
                 "algorithmic_flops_per_step": conv_flops}
-        # the other half of the BASELINE metric: parity of this very step against the oracle (checker only)
-        try:
-            from oracle import flame_oracle, nms_oracle
-
-            torch.cuda.synchronize()
-            off, cnt, idx = eng.head_offsets.cpu().numpy(), eng.keep_cnt.cpu().numpy(), eng.keep_idx.cpu().numpy()
-            n_chk = int(off[-1])
-            ids_ok = all(idx[b, :cnt[b]].tolist() == nms_oracle.select_nms(boxes[b].numpy(), scores[b].numpy(), CONF, IOU, TOPK, 100).tolist()
-                         for b in range(B))
-            err = 0.0
-            if n_chk:
-                p_chk, v_chk = eng.head_params(n_chk).cpu(), eng.head_verts(n_chk).cpu()
-                err = float((v_chk - flame_oracle.detector_vertices(p_chk, flame_oracle.load_flame_constants())).abs().max())
-            parity = {"vertices_3d_max_abs_err_px": err, "nms_ids_bit_exact": bool(ids_ok), "heads_checked": n_chk,
-                      "checker": "oracle/ on this step's own data: kept anchor ids vs the utils.nms restatement, vertices vs the FLAME "
-                                 "restatement applied to the device's 413-float rows (tolerance of the metric: 1e-4 px)"}
-        except Exception as ex:  # never lose the measurement line to the checker
-            parity = {"error": repr(ex)}
+        parity = parity_check(eng, boxes, scores, B)
         if world == 1:
             import torch as _t
 
