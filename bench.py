@@ -391,8 +391,6 @@ def run_ours(args, rank, world, local_rank):
                 "algorithmic_flops_per_step": conv_flops}
         parity = parity_check(eng, boxes, scores, B)
         if world == 1:
-            import torch as _t
-
             st = {}
             threads, cores = pick_cpu_threads(st)
             t0 = time.perf_counter()

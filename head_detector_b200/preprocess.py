@@ -2,8 +2,7 @@
 longest-side resize + centred border, bit-exact with the reference's cv2 calls, for a whole batch of
 differently sized images in one kernel launch (`vgh_letterbox`).  Host work left: packing the raw
 image bytes into one pinned buffer for a single H2D copy."""
-import ctypes as C
-from typing import List, Optional, Sequence, Tuple
+from typing import Optional, Sequence, Tuple
 
 import numpy as np
 import torch
