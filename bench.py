@@ -5,17 +5,18 @@
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
 
 A "step" = one pass of the whole path over one batch of synthetic input on every rank:
-uint8 images [32,640,640,3] per GPU -> conv backbone/neck/heads (tcgen05 implicit GEMM) -> box decode
+uint8 images [B,640,640,3] per GPU -> conv backbone/neck/heads (tcgen05 implicit GEMM) -> box decode
 -> engineered scores (~8 heads/image) -> select+NMS -> survivor FLAME rows ->
-fused FLAME decode to 5023-vertex meshes [-> NCCL gather of predictions to rank 0 when N > 1].
-Workload = the per-GPU shard of BASELINE configs[3] (batch 256 over 8 GPUs = 32/GPU, full path); it
-contains configs[1] (batch 32, backbone only) entirely.
+fused FLAME decode to 5023-vertex meshes [-> N > 1: the step's packed prediction record is stored straight
+into rank 0's receive ring over NVLink by the snapshot kernel (or sent with NCCL, --gather nccl)].
+Workload: BASELINE configs[2] (batch 64, full path, ~8 heads/image) on every GPU - weak scaling, so N = 8 processes a
+global batch of 512 per step (configs[3]'s batch-256 shard of 32/GPU: `--per-gpu-batch 32`).
 
 `value`  : device-timed (CUDA events, inputs resident in HBM, one CUDA-graph replay per step).
-`e2e`    : the same step through the host-buffer C-ABI call (vgh_detector_run_host): pinned host
+`e2e`    : the same step through the host-buffer C-ABI calls (vgh_detector_submit_host/collect_host): pinned host
            images -> H2D -> graph -> D2H of counts/boxes/scores/params/vertices, every step.
 `roofline`: conv_igemm kernel launches of one step timed live with CUDA-event pairs (eager pass),
-           algorithmic FLOPs (83.34 GMAC/img, deploy form) / that time.
+           executed FLOPs / that time (`frac`, `frac_serial`) and / the timed step (`frac_step`).
 """
 import argparse
 import json
@@ -29,7 +30,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-PER_GPU_BATCH = 32
+PER_GPU_BATCH = 64
 IMAGE_SIZE = 640
 HEADS_PER_IMAGE = 8
 CONF, IOU, TOPK = 0.5, 0.5, 1000
@@ -172,7 +173,7 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "images/sec (640x640)", "value": v, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": _config(args.gpus) | {"sample": f"{per_step} image(s) of the workload per step on the host CPU"},
+        "config": _config(args.gpus, args.per_gpu_batch),
         "cpu_baseline": {"value": v, "unit": "images/s", "cores": threads, "kind": "port", "host_cores": cores,
                          "sample": f"{per_step} image/step x {args.steps} steps, full path (deploy-form torch-CPU net + NMS + FLAME), {threads} threads (fastest of 8/16/32/64/{cores})"},
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -180,17 +181,18 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def _config(n, dense_heads=False):
+def _config(n, batch=PER_GPU_BATCH, dense_heads=False, gather=None):
     return {"heads": ("dense: FLAME branch of the heads computed on the whole feature maps" if dense_heads else
                       "sparse: FLAME branch of the heads (pose stem, towers, output convs) computed after NMS on 8x8 windows around the "
                       "survivors only - identical boxes / 413-float rows / vertices (tests/test_gpu_net.py::test_sparse_heads_match_dense_heads); "
-                      "`--dense-heads` runs the reference's dense graph (same box, back to back: 4740 images/s dense vs 5911 sparse, "
-                      "profiles/r1_sparse_ab_bench_dense_heads.json / r1_sparse_ab_bench_sparse_heads.json)"),
-            "workload": f"BASELINE configs[3] per-GPU shard: batch {PER_GPU_BATCH}/GPU x {n} GPU(s), {IMAGE_SIZE}x{IMAGE_SIZE} uint8 RGB, "
-                        f"VGGHeads_L full path (backbone+neck+heads, box decode, select+NMS, FLAME decode to 5023 verts), ~{HEADS_PER_IMAGE} heads/image; superset of configs[1]",
-            "global_batch": PER_GPU_BATCH * n, "image_size": IMAGE_SIZE, "heads_per_image": HEADS_PER_IMAGE,
-            "parallelism": f"dp{n} (batch-sharded, NCCL gather of predictions to rank 0)" if n > 1 else "single GPU",
-            "weights": "seeded random-init, deploy (re-parameterised) form", "in_flight": "2 batches per GPU (two detector handles on two streams)", "l2": "per-step working set ~5 GB >> 126 MB L2; 4 rotating input batches (157 MB)"}
+                      "the `dense_heads` key of this line is the same step with the reference's dense graph"),
+            "workload": f"BASELINE configs[2] per GPU: batch {batch}/GPU x {n} GPU(s), {IMAGE_SIZE}x{IMAGE_SIZE} uint8 RGB, "
+                        f"VGGHeads_L full path (backbone+neck+heads, box decode, select+NMS, FLAME decode to 5023 verts), ~{HEADS_PER_IMAGE} heads/image; "
+                        "superset of configs[1]; configs[3] = the same with --per-gpu-batch 32 on 8 GPUs",
+            "global_batch": batch * n, "image_size": IMAGE_SIZE, "heads_per_image": HEADS_PER_IMAGE,
+            "parallelism": (f"dp{n} (batch-sharded; predictions gathered to rank 0 every step: {gather})" if n > 1 else "single GPU"),
+            "weights": "seeded random-init, deploy (re-parameterised) form", "in_flight": "2 batches per GPU (two detector handles on two streams)",
+            "l2": f"per-step working set ~{0.157 * batch:.0f} GB >> 126 MB L2; 4 rotating input batches"}
 
 
 def parity_check(eng, boxes, scores, batch):
@@ -219,20 +221,128 @@ def parity_check(eng, boxes, scores, batch):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+class Pipeline:
+    """Two engines per GPU = two batches in flight: the select/NMS/FLAME tail of batch i (few, small kernels) overlaps
+    the stem / stage-1 kernels of batch i+1.  Every step is still one full pass over one batch.  N > 1: every step's
+    prediction record goes to rank 0 (parallel.PeerGather over NVLink peer memory, or parallel.RecordGather over NCCL)."""
+
+    def __init__(self, engs, dev_imgs, host_imgs, world, rank, gather_mode):
+        import torch
+
+        from head_detector_b200 import parallel
+
+        self.torch, self.engs, self.dev_imgs, self.host_imgs, self.world, self.rank = torch, engs, dev_imgs, host_imgs, world, rank
+        self.stream = torch.cuda.current_stream()
+        self.lanes = [torch.cuda.Stream() for _ in engs]
+        self.t = 0                       # this rank's step counter (identical on every rank)
+        self.peer = self.rg = None
+        self.gather = None
+        if world > 1:
+            layout = engs[0].record_layout()
+            if gather_mode in ("auto", "peer"):
+                try:
+                    self.peer = parallel.PeerGather(layout, depth=4)
+                    self.gather = "peer: pack kernel stores the record into rank 0's ring over NVLink (CUDA IPC), device-side flags, no host sync"
+                except parallel.PeerUnavailable as ex:
+                    if gather_mode == "peer":
+                        raise
+                    if rank == 0:
+                        print(f"bench.py: peer-memory gather unavailable ({ex}); using NCCL send/recv", file=sys.stderr, flush=True)
+            if self.peer is None:
+                self.rg = parallel.RecordGather(layout, lag=2)
+                self.gather = "nccl: local pack, counts all-gathered and read 2 steps late, exactly-sized send/recv"
+
+    # -- device-resident step (inputs in HBM)
+    def device_step(self, i):
+        torch = self.torch
+        k = i % len(self.engs)
+        e, lane = self.engs[k], self.lanes[k]
+        with torch.cuda.stream(lane):
+            e.input.copy_(self.dev_imgs[i % len(self.dev_imgs)], non_blocking=True)
+            if self.world == 1:
+                e.run_device(CONF, IOU, TOPK)
+            elif self.peer is not None:
+                self.peer.arm(e, self.t)
+                e.submit_device(CONF, IOU, TOPK)
+                if self.rank == 0:
+                    self.peer.consume(self.t)
+            else:
+                slot, rec = self.rg.acquire()
+                ev = self.rg.wait_event(slot)
+                if ev is not None:
+                    lane.wait_event(ev)
+                e.arm_push(rec.data_ptr())
+                e.submit_device(CONF, IOU, TOPK)
+                ready = torch.cuda.Event()
+                ready.record(lane)
+                self.rg.submit(slot, ready)
+        self.t += 1
+
+    def drain(self):
+        if self.rg is not None:
+            self.rg.flush(self.stream)
+        for l in self.lanes:
+            self.stream.wait_stream(l)
+        if self.peer is not None and self.rank == 0:
+            self.stream.wait_stream(self.peer.side)
+
+    # -- host-buffer steps (H2D + D2H inside), up to 3 in flight over the two engines
+    def host_steps(self, steps, out):
+        inflight = []
+
+        def collect():
+            e, slot = inflight.pop(0)
+            e.collect_host(out)
+            if slot is not None:
+                self.rg.submit(slot, None)   # the record was packed before the results were downloaded
+
+        for i in range(steps):
+            e = self.engs[i % len(self.engs)]
+            if len(inflight) >= 2 * len(self.engs) - 1:
+                collect()
+            slot = None
+            if self.peer is not None:
+                self.peer.arm(e, self.t)
+            elif self.rg is not None:
+                slot, rec = self.rg.acquire()
+                ev = self.rg.wait_event(slot)
+                if ev is not None:
+                    ev.synchronize()   # the send of 4 steps ago; never pending in practice
+                e.arm_push(rec.data_ptr())
+            e.submit_host(self.host_imgs[i % len(self.host_imgs)], CONF, IOU, TOPK)
+            if self.peer is not None and self.rank == 0:
+                self.peer.consume(self.t)
+            self.t += 1
+            inflight.append((e, slot))
+        while inflight:
+            collect()
+        self.drain()
+
+    def status(self):
+        st = 0
+        for e in self.engs:
+            st |= e.push_status()
+        if self.peer is not None and self.rank == 0:
+            st |= int(self.peer.status[0])
+        return st
+
+    def close(self):
+        if self.peer is not None:
+            self.peer.close()
+
+
 def run_ours(args, rank, world, local_rank):
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # many concurrent streams: keep their hardware queues apart
     import torch
     import torch.distributed as dist
 
-    from head_detector_b200 import arch, parallel, synth
+    from head_detector_b200 import arch, synth
     from head_detector_b200.engine import Engine
 
     torch.cuda.set_device(local_rank)
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    B = PER_GPU_BATCH
-    # Two engines per GPU = two batches in flight: the select/NMS/FLAME tail of batch i (few, small
-    # kernels) overlaps the stem / stage-1 kernels of batch i+1.  Every step is still one full pass
-    # over one batch; K steps are timed.
+    B = args.per_gpu_batch
     weights = arch.synthetic_weights(0)
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -246,46 +356,11 @@ def run_ours(args, rank, world, local_rank):
     ovr = (boxes.cuda(), scores.cuda())
     for e in engs:
         e.set_override(*ovr)
-        e.autotune(5)  # one-off per-layer kernel configuration search (setup, not timed)
+        if not args.no_autotune:
+            e.autotune(5)  # one-off per-layer kernel configuration search (setup, not timed)
     out = eng.alloc_host_outputs(B * 100)
-    stream = torch.cuda.current_stream()
-    lanes = [torch.cuda.Stream() for _ in engs]
-
-    # N > 1: the one exchange of the path - a ragged gather of predictions to rank 0 - runs on a side
-    # stream from a snapshot slot while the following steps compute (it is still part of every step)
-    side = torch.cuda.Stream() if world > 1 else None
-    pending = []
-
-    def finish_gather():
-        e, slot, ev = pending.pop(0)
-        with torch.cuda.stream(side):
-            side.wait_event(ev)
-            n = int(e.slot_total(slot)[0])
-            parallel.gather_predictions(e.slot_views(slot, n), n_heads=n)
-            e.release_slot(slot)
-
-    def device_step(i):
-        k = i % len(engs)
-        e = engs[k]
-        with torch.cuda.stream(lanes[k]):
-            e.input.copy_(dev_imgs[i % n_rot], non_blocking=True)
-            if world == 1:
-                e.run_device(CONF, IOU, TOPK)
-                return
-            slot = e.submit_device(CONF, IOU, TOPK)
-            ev = torch.cuda.Event()
-            ev.record()
-        pending.append((e, slot, ev))
-        if len(pending) > 1:
-            finish_gather()
-
-    def drain():
-        while pending:
-            finish_gather()
-        for l in lanes:
-            stream.wait_stream(l)
-        if side is not None:
-            stream.wait_stream(side)
+    pipe = Pipeline(engs, dev_imgs, host_imgs, world, rank, args.gather)
+    stream = pipe.stream
 
     def sync_all():
         torch.cuda.synchronize()
@@ -293,104 +368,85 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(step_fn, steps):
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t[0])
+        return x
+
+    def timed_device(steps):
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for l in lanes:
+        for l in pipe.lanes:
             l.wait_event(e0)
         for i in range(steps):
-            step_fn(i)
-        drain()
+            pipe.device_step(i)
+        pipe.drain()
         e1.record(stream)
         sync_all()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t[0])
-        return ms
+        return max_over_ranks(e0.elapsed_time(e1))
 
     for i in range(max(args.warmup, 3) + 1):
-        device_step(i)
-    drain()
+        pipe.device_step(i)
+    pipe.drain()
     sync_all()
     sampler.begin()
-    ms_dev = timed(device_step, args.steps)
+    ms_dev = timed_device(args.steps)
     sampler.end()
     heads_total = int(eng.head_offsets[-1])
 
-    # end to end through the host-buffer C-ABI: every step uploads its images from pinned host memory
-    # and downloads counts / boxes / scores / params / vertices: submit/collect pipeline over the two
-    # engines (copies of the neighbouring steps overlap compute); N > 1 adds the NCCL gather per step.
-    collected = {id(e): 0 for e in engs}
-
-    def collect_and_gather(e):
-        """Download the oldest batch of engine e; N > 1: then gather it to rank 0 from the snapshot slot
-        (device memory) on the side stream - the slot is handed back once the gather is queued."""
-        n = e.collect_host(out)
-        slot = collected[id(e)] & 1
-        collected[id(e)] += 1
-        if world > 1:
-            with torch.cuda.stream(side):
-                parallel.gather_predictions(e.slot_views(slot, n), n_heads=n)
-                e.release_slot(slot)
-
-    def pipelined_host(steps):
-        """K steps, up to 3 in flight over the two engines; returns after every result is on the host
-        (and, for N > 1, gathered on rank 0)."""
-        inflight = []
-        for i in range(steps):
-            e = engs[i % len(engs)]
-            if len(inflight) >= 2 * len(engs) - 1:
-                collect_and_gather(inflight.pop(0))
-            e.submit_host(host_imgs[i % n_rot], CONF, IOU, TOPK)
-            inflight.append(e)
-        while inflight:
-            collect_and_gather(inflight.pop(0))
-        if side is not None:
-            stream.wait_stream(side)
-
-    pipelined_host(4)
+    # end to end through the host-buffer C-ABI: every step uploads its images from pinned host memory and downloads
+    # counts / boxes / scores / params / vertices; N > 1: plus the gather of the step's record to rank 0
+    pipe.host_steps(4, out)
     sync_all()
     sampler.begin()
     t0 = time.perf_counter()
-    pipelined_host(args.steps)
+    pipe.host_steps(args.steps, out)
     sync_all()
-    e2e_s = time.perf_counter() - t0
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
     sampler.end()
     clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([e2e_s], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t[0])
     n_heads = int(out["total"][0])
     h2d = B * IMAGE_SIZE * IMAGE_SIZE * 3
     d2h = B * 4 + 4 + B * 100 * 16 + B * 100 * 4 + n_heads * (413 * 4 + 5023 * 12)
+    gather_status = pipe.status()
+    gathered_heads = None
+    if pipe.peer is not None and rank == 0:
+        gathered_heads = int(pipe.peer.totals[(pipe.t - 1) % pipe.peer.depth])
+    elif pipe.rg is not None and rank == 0 and pipe.rg.last_counts is not None:
+        gathered_heads = int(sum(pipe.rg.last_counts))
+    if gather_status:
+        raise RuntimeError(f"rank {rank}: prediction gather timed out (status bits {gather_status}: 1 = producer waited for a slot, 2 = consumer waited for a record)")
 
-    # live roofline of the dominant kernel (conv_igemm): event pairs around every launch of one step
-    roof = None
-    parity = None
-    cpu_base = None
+    line = None
     if rank == 0:
+        # live roofline of the dominant kernel (conv_igemm): event pairs around every launch of one step (eager pass)
         rows = eng.profile(iters=3, conf=CONF, iou=IOU, top_k=TOPK)
         conv_ms = sum(t for _, t, f in rows if f > 0)
         conv_flops = sum(f for _, t, f in rows if f > 0)
         all_ms = sum(t for _, t, _ in rows)
         pk = _peaks()
         ach = conv_flops / (conv_ms * 1e-3) / 1e12
+        step_ms = ms_dev / args.steps
         dense_flops = 2 * arch.total_macs(IMAGE_SIZE) * B
         roof = {"bound": "tensor", "kernel": f"conv_igemm_swap_kernel / conv_igemm_kernel ({sum(1 for _, t, f in rows if f > 0)} dense launches/step)",
                 "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s",
                 "flops_note": "EXECUTED conv FLOPs of the dense launches / their summed durations" + ("" if args.dense_heads else
                               f"; the reference graph's {dense_flops / 1e12:.2f} TFLOP/step include {100 * (1 - conv_flops / dense_flops):.0f} % "
                               "of FLAME-branch work at anchors NMS discards, which this build does not execute (and does not count)"),
-                "frac": ach / pk["tflops"], "peak_source": pk["src"], "traffic": ncu_conv_traffic(args.dense_heads),
-                "traffic_note": "DRAM bytes of all conv_igemm launches of one step (ncu launch list of the same step under profiles/: r1_sparse_ncu_launches.csv, or r1_xr_ncu_launches_metrics.csv with --dense-heads); algorithmic activation bytes are ~13 GB/step",
+                "frac": ach / pk["tflops"], "frac_serial": ach / pk["tflops"],
+                "frac_step": conv_flops / (step_ms * 1e-3) / 1e12 / pk["tflops"],
+                "frac_note": "frac = frac_serial: executed FLOPs / summed event durations of the conv launches in a serial eager pass; "
+                             "frac_step: the same FLOPs / ms_per_step of the timed CUDA-graph region (all kernels of the step, two batches overlapping)",
+                "peak_source": pk["src"], "traffic": ncu_conv_traffic(args.dense_heads),
+                "traffic_note": "DRAM bytes of all conv_igemm launches of one step from the committed ncu launch list (profiles/); algorithmic activation bytes are ~0.41 GB/image",
                 "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_ms / all_ms,
                 "algorithmic_flops_per_step": conv_flops}
         parity = parity_check(eng, boxes, scores, B)
-        if world == 1:
+        cpu_base = None
+        if world == 1 and not args.no_cpu_baseline:
             st = {}
             threads, cores = pick_cpu_threads(st)
             t0 = time.perf_counter()
@@ -403,24 +459,75 @@ def run_ours(args, rank, world, local_rank):
             dt = time.perf_counter() - t0
             cpu_base = {"value": n_img / dt, "unit": "images/s", "cores": threads, "kind": "port", "host_cores": cores,
                         "sample": f"{n_img} images of the same workload (deploy-form torch-CPU fp32 network + utils.nms + FLAME decode restatements), {threads} threads (fastest of 8/16/32/64/{cores})"}
-    if rank == 0:
         imgs = B * world * args.steps
         line = {
             "metric": "images/sec (640x640)", "value": imgs / (ms_dev * 1e-3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": _config(world, args.dense_heads),
+            "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": _config(world, B, args.dense_heads, pipe.gather),
             "clocks": clocks,
             "e2e": {"value": imgs / e2e_s, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "mode": "vgh_detector_submit_host/collect_host over 2 detector handles (3 batches in flight)" + (" + NCCL gather of every step" if world > 1 else "")},
-            "gpu_launches": eng.launch_count * args.steps,
+                    "mode": "vgh_detector_submit_host/collect_host over 2 detector handles (3 batches in flight)" + (" + gather of every step's record to rank 0" if world > 1 else "")},
+            "gpu_launches": (eng.launch_count + (0 if world == 1 else 1)) * args.steps,
             "roofline": roof, "cpu_baseline": cpu_base, "parity": parity,
             "heads_per_step_per_gpu": heads_total,
             "conv_gflop_per_image": 2 * arch.total_macs(IMAGE_SIZE) / 1e9,
         }
+        if world > 1:
+            line["gather"] = {"transport": pipe.gather, "heads_gathered_last_step": gathered_heads, "status": gather_status}
+    pipe.close()
+    del pipe
+    if rank == 0 and world == 1 and not args.dense_heads and not args.no_extras:
+        for e in engs:
+            e.__del__()
+        engs.clear()
+        torch.cuda.empty_cache()
+        try:
+            line["dense_heads"] = extra_dense(args, weights, B)
+        except Exception as ex:  # never lose the headline to an extra
+            line["dense_heads"] = {"error": repr(ex)}
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        if not args.keep_process_group:
+            dist.destroy_process_group()
+    return line
+
+
+def extra_dense(args, weights, B):
+    """The same step with the reference's dense graph (FLAME branch on the whole maps): the apples-to-apples figure
+    against the reference's own network, device-timed the same way (fewer steps)."""
+    import torch
+
+    from head_detector_b200 import synth
+    from head_detector_b200.engine import Engine
+
+    engs = [Engine(weights, B, IMAGE_SIZE, sparse_heads=False) for _ in range(2)]
+    boxes, scores = synth.engineered_heads(B, engs[0].A, IMAGE_SIZE, HEADS_PER_IMAGE, seed=7)
+    ovr = (boxes.cuda(), scores.cuda())
+    imgs = [synth.synthetic_images(B, IMAGE_SIZE, seed=i).cuda() for i in range(4)]
+    for e in engs:
+        e.set_override(*ovr)
+        if not args.no_autotune:
+            e.autotune(3)
+    pipe = Pipeline(engs, imgs, None, 1, 0, "auto")
+    steps = max(6, min(args.steps, 12))
+    for i in range(4):
+        pipe.device_step(i)
+    pipe.drain()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(pipe.stream)
+    for l in pipe.lanes:
+        l.wait_event(e0)
+    for i in range(steps):
+        pipe.device_step(i)
+    pipe.drain()
+    e1.record(pipe.stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    return {"value": B * steps / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms / steps, "steps": steps,
+            "note": "--dense-heads: full reference graph (166.68 GFLOP/image), same inputs, device-timed"}
 
 
 def main():
@@ -429,9 +536,16 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--per-gpu-batch", type=int, default=PER_GPU_BATCH, help="images per GPU per step (64 = BASELINE configs[2]; 32 = the configs[3] shard)")
+    ap.add_argument("--gather", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N > 1: transport of the per-step prediction gather to rank 0 (auto = NVLink peer memory, NCCL if IPC is unavailable)")
     ap.add_argument("--dense-heads", action="store_true",
                     help="run the FLAME branch of the heads on the whole feature maps (as the reference graph does) instead of on the "
                          "8x8 windows around the NMS survivors; same predictions, ~20 %% more work")
+    ap.add_argument("--no-autotune", action="store_true", help="skip the per-layer configuration search (tests)")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg of the N=1 line (tests)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra dense-heads measurement of the N=1 line")
+    ap.add_argument("--keep-process-group", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -445,7 +559,14 @@ def main():
         raise SystemExit("bench.py: no CUDA device - the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
     if world == 1 and args.gpus > 1:
         raise SystemExit("launch multi-GPU runs with torch.distributed.run (one process per GPU)")
-    run_ours(args, rank, world, local_rank)
+    try:
+        run_ours(args, rank, world, local_rank)
+    except BaseException:
+        import traceback
+
+        sys.stderr.write(f"rank {rank}: bench.py failed\n" + "".join(f"rank {rank}: {l}" for l in traceback.format_exc().splitlines(True)))
+        sys.stderr.flush()
+        raise
 
 
 if __name__ == "__main__":

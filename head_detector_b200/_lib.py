@@ -67,9 +67,16 @@ _SIGS = {
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "vgh_detector_submit_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int]),
     "vgh_detector_collect_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
-    "vgh_detector_submit_device": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p]),
-    "vgh_detector_release_slot": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
-    "vgh_detector_slot_output": (C.c_void_p, [C.c_void_p, C.c_int, C.c_int]),
+    "vgh_detector_submit_device": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_void_p]),
+    "vgh_detector_record_layout": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vgh_detector_arm_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]),
+    "vgh_detector_push_status": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vgh_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]),
+    "vgh_peer_free": (C.c_int, [C.c_void_p]),
+    "vgh_peer_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "vgh_peer_close": (C.c_int, [C.c_void_p]),
+    "vgh_gather_wait": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_int64, C.c_void_p, C.c_uint64,
+                                  C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "vgh_detector_run_device": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_void_p]),
     "vgh_detector_set_override": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "vgh_detector_profile": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),

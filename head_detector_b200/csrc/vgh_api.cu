@@ -13,6 +13,7 @@
 #include "aux_kernels.cuh"
 #include "conv_igemm.cuh"
 #include "flame_decode.cuh"
+#include "gather.cuh"
 #include "letterbox.cuh"
 #include "select_nms.cuh"
 
@@ -129,7 +130,18 @@ struct vgh_detector {
     bool busy = false;
   } slots[2];
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr, pipe_stream = nullptr;
-  int submit_idx = 0, collect_idx = 0;
+  int submit_idx = 0, collect_idx = 0;  // host pipeline only: submit_host advances one, collect_host the other
+  // multi-GPU record push (vgh_detector_arm_push): destination of the NEXT submit's packed result record
+  struct Push {
+    bool armed = false;
+    float* dst = nullptr;
+    const unsigned long long* wait_flag = nullptr;
+    unsigned long long wait_val = 0;
+    unsigned long long* done_flag = nullptr;
+    unsigned long long done_val = 0;
+  } push;
+  int *push_counter = nullptr, *push_status = nullptr;  // device: block counter of the pack kernel / sticky time-out bits
+  uint32_t push_seq = 0;
   std::vector<cudaStream_t> lane_streams;  // side streams for independent graph branches (lanes 1..)
   std::vector<cudaEvent_t> op_events;
   cudaEvent_t phase_event = nullptr;
@@ -388,7 +400,8 @@ extern "C" void vgh_detector_destroy(vgh_detector* d) {
   for (void* p : d->buf_ptr) cudaFree(p);
   void* ptrs[] = {d->weights, d->bias, d->input, d->boxes, d->scores, d->keep_boxes,
                   d->keep_scores, d->keep_idx, d->keep_cnt, d->offsets, d->head_img, d->params, d->head_xform,
-                  d->verts, d->rot, d->img_xform, d->head_level, d->head_patch, d->patch_src, d->level_rows};
+                  d->verts, d->rot, d->img_xform, d->head_level, d->head_patch, d->patch_src, d->level_rows, d->push_counter,
+                  d->push_status};
   for (void* p : ptrs) cudaFree(p);
   delete d;
 }
@@ -476,7 +489,8 @@ extern "C" int vgh_detector_create(const vgh_net_desc* n, const vgh_flame* flame
       dmalloc(&d->keep_cnt, B) != cudaSuccess || dmalloc(&d->offsets, B + 1) != cudaSuccess ||
       dmalloc(&d->head_img, cap) != cudaSuccess || dmalloc(&d->params, cap * VGH_NUM_PARAMS) != cudaSuccess ||
       dmalloc(&d->head_xform, cap * 3) != cudaSuccess || dmalloc(&d->verts, cap * VGH_NUM_VERTS * 3) != cudaSuccess ||
-      dmalloc(&d->rot, cap * 9) != cudaSuccess || dmalloc(&d->img_xform, B * 3) != cudaSuccess)
+      dmalloc(&d->rot, cap * 9) != cudaSuccess || dmalloc(&d->img_xform, B * 3) != cudaSuccess ||
+      dmalloc(&d->push_counter, 1) != cudaSuccess || dmalloc(&d->push_status, 1) != cudaSuccess)
     return bail(fail(4, "result buffer allocation failed"));
   {
     std::vector<float> xf(B * 3, 0.f);
@@ -986,6 +1000,7 @@ extern "C" int vgh_detector_run_host(vgh_detector* d, const uint8_t* images_host
 // Two-deep software pipeline over HOST buffers: while step i computes, the images of step i+1 are
 // uploaded and the results of step i-1 are downloaded (separate copy streams, double-buffered staging
 // on the device).  Every step still performs its own H2D and D2H copies; they just overlap compute.
+static int push_if_armed(vgh_detector* d, cudaStream_t s);
 static int ensure_pipeline(vgh_detector* d) {
   if (d->pipe_stream) return 0;
   CUDA_OK(cudaStreamCreateWithFlags(&d->pipe_stream, cudaStreamNonBlocking));
@@ -1031,6 +1046,8 @@ extern "C" int vgh_detector_submit_host(vgh_detector* d, const uint8_t* images_h
   if (copy_rows_launch(d->params, sl.params, d->offsets + B, VGH_NUM_PARAMS, (int)(B * K), s) ||
       copy_rows_launch(d->verts, sl.verts, d->offsets + B, VGH_NUM_VERTS * 3, (int)(B * K), s))
     return fail(5, "result staging launch failed");
+  rc = push_if_armed(d, s);  // multi-GPU: this step's record goes to rank 0 from the live buffers (before the next replay)
+  if (rc) return rc;
   CUDA_OK(cudaEventRecord(sl.compute_done, s));
   sl.busy = true;
   ++d->submit_idx;
@@ -1065,51 +1082,95 @@ extern "C" int vgh_detector_collect_host(vgh_detector* d, int32_t* keep_cnt_host
   return 0;
 }
 
-// Device-resident variant of the pipeline for multi-GPU runs: replays the graph on `stream` over the
-// image already in the staging input and snapshots the results into a slot, so that the NCCL gather of
-// this step can run (on another stream) while the next step computes.  The consumer hands the slot
-// back with vgh_detector_release_slot(slot, its_stream).
-extern "C" int vgh_detector_submit_device(vgh_detector* d, float conf_thr, float iou_thr, int top_k, void* stream,
-                                          int32_t* slot_out) {
-  if (!d || !slot_out) return fail(1, "null argument");
-  int rc = ensure_pipeline(d);
-  if (rc) return rc;
+// ------------------------------------------------------------------------------------------ multi-GPU record push
+static int push_timeout_ms() {
+  const char* e = getenv("VGGHEADS_B200_PUSH_TIMEOUT_MS");
+  const int v = e ? atoi(e) : 0;
+  return v > 0 ? v : 4000;
+}
+// Packs the live results into the armed destination on stream s (after the graph replay queued there) and disarms.
+static int push_if_armed(vgh_detector* d, cudaStream_t s) {
+  if (!d->push.armed) return 0;
+  d->push.armed = false;
+  RecordSrc src{d->keep_cnt, d->offsets + d->B, d->keep_boxes, d->keep_scores, d->params, d->verts};
+  if (record_push_launch(src, record_layout(d->B, d->keep_k), d->push_seq++, d->push.dst, d->push.wait_flag, d->push.wait_val,
+                         d->push.done_flag, d->push.done_val, d->push_counter, d->push_status, push_timeout_ms(), s))
+    return fail(5, "record push launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return 0;
+}
+
+extern "C" int vgh_detector_record_layout(const vgh_detector* d, int64_t* out4) {
+  if (!d || !out4) return fail(1, "null argument");
+  const RecordLayout l = record_layout(d->B, d->keep_k);
+  out4[0] = l.fixed_words; out4[1] = VGH_NUM_PARAMS; out4[2] = VGH_NUM_VERTS * 3; out4[3] = l.capacity_words;
+  return 0;
+}
+extern "C" int vgh_detector_arm_push(vgh_detector* d, float* dst_record_dev, const uint64_t* wait_flag_dev, uint64_t wait_val,
+                                     uint64_t* done_flag_dev, uint64_t done_val) {
+  if (!d || !dst_record_dev) return fail(1, "null argument");
+  if (reinterpret_cast<uintptr_t>(dst_record_dev) % 16) return fail(1, "record destination must be 16-byte aligned");
+  d->push.armed = true;
+  d->push.dst = dst_record_dev;
+  d->push.wait_flag = reinterpret_cast<const unsigned long long*>(wait_flag_dev);
+  d->push.wait_val = wait_val;
+  d->push.done_flag = reinterpret_cast<unsigned long long*>(done_flag_dev);
+  d->push.done_val = done_val;
+  return 0;
+}
+extern "C" int vgh_detector_push_status(vgh_detector* d, int32_t* status_host) {
+  if (!d || !status_host) return fail(1, "null argument");
+  CUDA_OK(cudaMemcpy(status_host, d->push_status, 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+// Device-resident step for multi-GPU runs: graph replay over the staging input on `stream`, then - if a push is armed -
+// ONE kernel packs the step's result record straight into its destination (local snapshot or rank 0's peer ring).
+extern "C" int vgh_detector_submit_device(vgh_detector* d, float conf_thr, float iou_thr, int top_k, void* stream) {
+  if (!d) return fail(1, "null argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  rc = ensure_graph(d, conf_thr, iou_thr, top_k, s);
+  int rc = ensure_graph(d, conf_thr, iou_thr, top_k, s);
   if (rc) return rc;
-  const int slot = d->submit_idx & 1;
-  vgh_detector::Slot& sl = d->slots[slot];
-  const size_t B = d->B, K = d->keep_k;
   CUDA_OK(cudaGraphLaunch(d->graph, s));
-  CUDA_OK(cudaStreamWaitEvent(s, sl.d2h_done, 0));  // previous consumer of this slot is done
-  CUDA_OK(cudaMemcpyAsync(sl.cnt, d->keep_cnt, B * 4, cudaMemcpyDeviceToDevice, s));
-  CUDA_OK(cudaMemcpyAsync(sl.total, d->offsets + B, 4, cudaMemcpyDeviceToDevice, s));
-  CUDA_OK(cudaMemcpyAsync(sl.kboxes, d->keep_boxes, B * K * 16, cudaMemcpyDeviceToDevice, s));
-  CUDA_OK(cudaMemcpyAsync(sl.kscores, d->keep_scores, B * K * 4, cudaMemcpyDeviceToDevice, s));
-  if (copy_rows_launch(d->params, sl.params, d->offsets + B, VGH_NUM_PARAMS, (int)(B * K), s) ||
-      copy_rows_launch(d->verts, sl.verts, d->offsets + B, VGH_NUM_VERTS * 3, (int)(B * K), s))
-    return fail(5, "result staging launch failed");
-  ++d->submit_idx;
-  *slot_out = slot;
+  return push_if_armed(d, s);
+}
+
+// ------------------------------------------------------------------------------------------ peer memory (CUDA IPC)
+extern "C" int vgh_peer_alloc(size_t bytes, void** dev_ptr, uint8_t* handle64) {
+  if (!dev_ptr || !handle64 || bytes == 0) return fail(1, "bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  void* p = nullptr;
+  CUDA_OK(cudaMalloc(&p, bytes));
+  cudaError_t e = cudaMemset(p, 0, bytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) { cudaFree(p); return fail(100, "peer alloc: %s", cudaGetErrorString(e)); }
+  memcpy(handle64, &h, 64);
+  *dev_ptr = p;
   return 0;
 }
-extern "C" int vgh_detector_release_slot(vgh_detector* d, int slot, void* consumer_stream) {
-  if (!d || slot < 0 || slot > 1 || !d->pipe_stream) return fail(1, "bad slot");
-  CUDA_OK(cudaEventRecord(d->slots[slot].d2h_done, static_cast<cudaStream_t>(consumer_stream)));
+extern "C" int vgh_peer_free(void* dev_ptr) {
+  if (dev_ptr) CUDA_OK(cudaFree(dev_ptr));
   return 0;
 }
-// which: VGH_OUT_KEEP_CNT, VGH_OUT_KEEP_BOXES, VGH_OUT_KEEP_SCORES, VGH_OUT_HEAD_PARAMS, VGH_OUT_HEAD_VERTS,
-// VGH_OUT_HEAD_OFFSETS (-> int32[1] total heads)
-extern "C" void* vgh_detector_slot_output(vgh_detector* d, int slot, int which) {
-  if (!d || slot < 0 || slot > 1 || !d->pipe_stream) return nullptr;
-  vgh_detector::Slot& sl = d->slots[slot];
-  switch (which) {
-    case VGH_OUT_KEEP_CNT: return sl.cnt;
-    case VGH_OUT_KEEP_BOXES: return sl.kboxes;
-    case VGH_OUT_KEEP_SCORES: return sl.kscores;
-    case VGH_OUT_HEAD_PARAMS: return sl.params;
-    case VGH_OUT_HEAD_VERTS: return sl.verts;
-    case VGH_OUT_HEAD_OFFSETS: return sl.total;
-  }
-  return nullptr;
+extern "C" int vgh_peer_open(const uint8_t* handle64, void** dev_ptr) {
+  if (!handle64 || !dev_ptr) return fail(1, "null argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  cudaError_t e = cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(101, "cudaIpcOpenMemHandle: %s", cudaGetErrorString(e)); }
+  return 0;
+}
+extern "C" int vgh_peer_close(void* dev_ptr) {
+  if (dev_ptr) CUDA_OK(cudaIpcCloseMemHandle(dev_ptr));
+  return 0;
+}
+extern "C" int vgh_gather_wait(const uint64_t* ready_dev, int n, int stride, uint64_t value, const float* records_dev,
+                               int64_t record_stride_words, uint64_t* const* ack_ptrs_dev, uint64_t ack_val, int32_t* total_out_dev,
+                               int32_t* status_dev, int timeout_ms, void* stream) {
+  if (!ready_dev || n < 1 || n > 32) return fail(1, "bad argument");
+  if (gather_wait_launch(reinterpret_cast<const unsigned long long*>(ready_dev), n, stride, value, records_dev, record_stride_words,
+                         reinterpret_cast<unsigned long long* const*>(ack_ptrs_dev), ack_val, total_out_dev, status_dev,
+                         timeout_ms > 0 ? timeout_ms : push_timeout_ms(), static_cast<cudaStream_t>(stream)))
+    return fail(5, "gather wait launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return 0;
 }

@@ -148,25 +148,26 @@ class Engine:
             out["verts"].data_ptr(), out["verts"].shape[0], total.data_ptr(), _lib.stream_ptr()), "run_host")
         return int(total[0])
 
-    def submit_device(self, conf=0.5, iou=0.5, top_k=1000) -> int:
-        """Graph replay over the staging input + snapshot of the results into a slot (returned)."""
-        slot = C.c_int32(-1)
-        _lib.check(_lib.lib().vgh_detector_submit_device(self._h, conf, iou, top_k, _lib.stream_ptr(), C.byref(slot)), "submit_device")
-        return slot.value
+    # -- multi-GPU: packed result records (include/vggheads_b200.h "multi-GPU gather")
+    def record_layout(self) -> dict:
+        out = (C.c_int64 * 4)()
+        _lib.check(_lib.lib().vgh_detector_record_layout(self._h, out), "record_layout")
+        return {"B": self.B, "K": self.keep_k, "fixed_words": out[0], "param_words": out[1], "vert_words": out[2], "capacity_words": out[3]}
 
-    def slot_views(self, slot: int, n_heads: int):
-        """Zero-copy views of a snapshot slot: dict(keep_cnt, boxes, scores, params, verts)."""
-        def v(which, shape, ts="<f4"):
-            return torch.as_tensor(_DevView(_lib.lib().vgh_detector_slot_output(self._h, slot, which), shape, ts), device="cuda")
-        return {"keep_cnt": v(_lib.OUT_KEEP_CNT, (self.B,), "<i4"), "boxes": v(_lib.OUT_KEEP_BOXES, (self.B * self.keep_k, 4)),
-                "scores": v(_lib.OUT_KEEP_SCORES, (self.B * self.keep_k,)), "params": v(_lib.OUT_HEAD_PARAMS, (max(n_heads, 1), _lib.NUM_PARAMS))[:n_heads],
-                "verts": v(_lib.OUT_HEAD_VERTS, (max(n_heads, 1), _lib.NUM_VERTS, 3))[:n_heads]}
+    def arm_push(self, dst_ptr: int, wait_flag: int = 0, wait_val: int = 0, done_flag: int = 0, done_val: int = 0):
+        """The next submit_device / submit_host packs its result record into `dst_ptr` (local or peer-mapped device
+        memory) after waiting on the device for *wait_flag >= wait_val, then sets *done_flag = done_val."""
+        _lib.check(_lib.lib().vgh_detector_arm_push(self._h, C.c_void_p(dst_ptr), C.c_void_p(wait_flag or None), wait_val,
+                                                    C.c_void_p(done_flag or None), done_val), "arm_push")
 
-    def slot_total(self, slot: int) -> torch.Tensor:
-        return torch.as_tensor(_DevView(_lib.lib().vgh_detector_slot_output(self._h, slot, _lib.OUT_HEAD_OFFSETS), (1,), "<i4"), device="cuda")
+    def submit_device(self, conf=0.5, iou=0.5, top_k=1000):
+        """Graph replay over the staging input on the current stream (+ the armed record push)."""
+        _lib.check(_lib.lib().vgh_detector_submit_device(self._h, conf, iou, top_k, _lib.stream_ptr()), "submit_device")
 
-    def release_slot(self, slot: int):
-        _lib.check(_lib.lib().vgh_detector_release_slot(self._h, slot, _lib.stream_ptr()), "release_slot")
+    def push_status(self) -> int:
+        st = C.c_int32(0)
+        _lib.check(_lib.lib().vgh_detector_push_status(self._h, C.byref(st)), "push_status")
+        return st.value
 
     def submit_host(self, images_host: torch.Tensor, conf=0.5, iou=0.5, top_k=1000):
         """Pipelined end-to-end: enqueue upload + compute + result staging of one batch (max 2 in flight)."""

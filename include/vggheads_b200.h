@@ -177,14 +177,43 @@ int vgh_detector_run_host(vgh_detector* d, const uint8_t* images_host, const flo
 int vgh_detector_submit_host(vgh_detector* d, const uint8_t* images_host, float conf_thr, float iou_thr, int top_k);
 int vgh_detector_collect_host(vgh_detector* d, int32_t* keep_cnt_host, float* keep_boxes_host, float* keep_scores_host,
                               float* params_host, float* verts_host, int max_heads, int32_t* total_heads);
-/* Device-resident pipeline step for multi-GPU runs: graph replay over the staging input + snapshot of
- * the results into one of two slots (returned in *slot_out), so that the gather of this step can run
- * on another stream while the next step computes.  vgh_detector_slot_output(slot, VGH_OUT_*) gives the
- * snapshot pointers (KEEP_CNT, KEEP_BOXES, KEEP_SCORES, HEAD_PARAMS, HEAD_VERTS, HEAD_OFFSETS -> total);
- * vgh_detector_release_slot(slot, consumer_stream) hands the slot back once the consumer's work is queued. */
-int vgh_detector_submit_device(vgh_detector* d, float conf_thr, float iou_thr, int top_k, void* stream, int32_t* slot_out);
-int vgh_detector_release_slot(vgh_detector* d, int slot, void* consumer_stream);
-void* vgh_detector_slot_output(vgh_detector* d, int slot, int which);
+/* ---------------------------------------------------------------------------------- multi-GPU gather
+ * The reference is single-GPU; its batched twin (yolo_heads_post_prediction_callback.py:55-97) treats every image
+ * independently, so the batch is sharded over ranks (one process per GPU) and the one exchange of the path is the
+ * gather of every rank's predictions to rank 0 (BASELINE north_star).  Here that exchange is fused into
+ * the per-step result snapshot: ONE kernel packs the step's results into a RECORD and writes it straight into its
+ * destination - a local buffer, or rank 0's receive ring mapped over NVLink (vgh_peer_*), with device-side flags for
+ * flow control; no size exchange and no host synchronisation.
+ *
+ * Record (4-byte words; n = heads of the step): [0] n, [1] B, [2] keep_k, [3] sequence, [4..15] reserved,
+ * keep_cnt int32[B] (padded to 4 words), keep_boxes float[B,keep_k,4], keep_scores float[B,keep_k] (padded to 4) ->
+ * `fixed_words`; then params float[n,413] (padded to 4), then vertices float[n,5023,3].
+ * vgh_detector_record_layout: out4 = {fixed_words, 413, 15069, capacity_words (n = B*keep_k)}. */
+int vgh_detector_record_layout(const vgh_detector* d, int64_t* out4);
+/* Arms the NEXT vgh_detector_submit_device / vgh_detector_submit_host: after that step's graph replay its record is
+ * packed into dst_record_dev (16-byte aligned, capacity_words words; local or peer-mapped).  wait_flag_dev (optional,
+ * device memory): the pack first waits on the device until *wait_flag_dev >= wait_val (slot handed back by the
+ * consumer; bounded by $VGGHEADS_B200_PUSH_TIMEOUT_MS, default 4000 -> sticky bit 1 in vgh_detector_push_status).
+ * done_flag_dev (optional, may be peer memory): set to done_val once the whole record is visible system-wide. */
+int vgh_detector_arm_push(vgh_detector* d, float* dst_record_dev, const uint64_t* wait_flag_dev, uint64_t wait_val,
+                          uint64_t* done_flag_dev, uint64_t done_val);
+int vgh_detector_push_status(vgh_detector* d, int32_t* status_host);
+/* Device-resident step: graph replay over the internal staging input on `stream` (+ the armed record push). */
+int vgh_detector_submit_device(vgh_detector* d, float conf_thr, float iou_thr, int top_k, void* stream);
+/* Peer memory through CUDA IPC (one process per GPU): alloc returns a zeroed device allocation and its 64-byte handle;
+ * another process opens the handle (peer access over NVLink is enabled lazily) and may hand the pointer to
+ * vgh_detector_arm_push as destination / flag. */
+int vgh_peer_alloc(size_t bytes, void** dev_ptr, uint8_t* handle64);
+int vgh_peer_free(void* dev_ptr);
+int vgh_peer_open(const uint8_t* handle64, void** dev_ptr);
+int vgh_peer_close(void* dev_ptr);
+/* Consumer (rank 0): a one-block kernel on `stream` waits until ready_dev[i*stride] >= value for all i < n (n <= 32;
+ * bounded by timeout_ms, 0 = default -> bit 2 of *status_dev), stores the sum of the n records' head counts (record i
+ * at records_dev + i*record_stride_words; NULL = skip) to *total_out_dev, then writes ack_val to every ack_ptrs_dev[i]
+ * (device array of n device-accessible pointers, typically peer memory; NULL entries skipped). */
+int vgh_gather_wait(const uint64_t* ready_dev, int n, int stride, uint64_t value, const float* records_dev,
+                    int64_t record_stride_words, uint64_t* const* ack_ptrs_dev, uint64_t ack_val, int32_t* total_out_dev,
+                    int32_t* status_dev, int timeout_ms, void* stream);
 /* Same device work (graph replay) with inputs already resident in the internal staging buffer and
  * results left on the device - the kernel-only timing path. */
 int vgh_detector_run_device(vgh_detector* d, float conf_thr, float iou_thr, int top_k, void* stream);
