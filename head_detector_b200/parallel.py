@@ -252,17 +252,23 @@ class PeerGather:
         at = self.rank * self.depth + s
         eng.arm_push(self.ring_ptr + at * self.words * 4, self.ack_ptr + 8 * s, t // self.depth, self.ready_ptr + 8 * at, t + 1)
 
-    def consume(self, t: int):
-        """Rank 0: queue the consumer of step t on the side stream (waits for every rank's flag, sums the head counts,
-        hands the slots back).  No host synchronisation."""
+    def consume(self, t: int, ack: bool = True):
+        """Rank 0: queue the consumer of step t on the side stream: a one-block kernel waits for every rank's flag and sums
+        the head counts into `totals[t % depth]`; with `ack` it then hands the slots back to the producers.  A consumer
+        that reads the records (copy-out, D2H ...) passes ack=False, queues its reads on `side`, then calls `ack(t)`.
+        No host synchronisation."""
         from . import _lib
 
         s = t % self.depth
         _lib.check(self.lib.vgh_gather_wait(C.c_void_p(self.ready_ptr + 8 * s), self.world, self.depth, t + 1,
                                             C.c_void_p(self.ring_ptr + s * self.words * 4), self.depth * self.words,
-                                            C.c_void_p(self.ack_table[s].data_ptr()), t // self.depth + 1,
+                                            C.c_void_p(self.ack_table[s].data_ptr()) if ack else None, t // self.depth + 1,
                                             C.c_void_p(self.totals[s:].data_ptr()), C.c_void_p(self.status.data_ptr()), self.timeout_ms,
                                             C.c_void_p(self.side.cuda_stream)), "vgh_gather_wait")
+
+    def ack(self, t: int):
+        """Rank 0: hand the slots of step t back (after the reads queued on `side`)."""
+        self.consume(t, ack=True)
 
     def record(self, rank: int, t: int) -> torch.Tensor:
         """Rank 0: the record rank `rank` pushed for step t (valid until the slot is reused `depth` steps later)."""

@@ -208,11 +208,16 @@ def _gather_worker(rank, world, q, transport, steps):
                 pg.arm(e, t)
                 e.submit_device(CONF, IOU, TOPK)
             if rank == 0:
-                pg.consume(t)
-                if t % 4 == 3 or t == steps - 1:   # look at the ring now and then (host sync only in the test)
-                    pg.side.synchronize()
+                if t % 4 == 3 or t == steps - 1:   # a consumer that reads the records: wait, copy out on `side`, then hand the slots back
+                    pg.consume(t, ack=False)
+                    with torch.cuda.stream(pg.side):
+                        recs = [pg.record(r, t).clone() for r in range(world)]
+                    pg.ack(t)
+                    pg.side.synchronize()          # (host sync only in the test)
                     assert int(pg.totals[t % pg.depth]) == sum(expect[r][t % 2]["params"].shape[0] for r in range(world))
-                    check(t, [pg.record(r, t) for r in range(world)])
+                    check(t, recs)
+                else:
+                    pg.consume(t)
         torch.cuda.synchronize()
         st = sum(e.push_status() for e in engs) + (int(pg.status[0]) if rank == 0 else 0)
         pg.close()
