@@ -191,7 +191,7 @@ def _config(n, batch=PER_GPU_BATCH, dense_heads=False, gather=None):
                         "superset of configs[1]; configs[3] = the same with --per-gpu-batch 32 on 8 GPUs",
             "global_batch": batch * n, "image_size": IMAGE_SIZE, "heads_per_image": HEADS_PER_IMAGE,
             "parallelism": (f"dp{n} (batch-sharded; predictions gathered to rank 0 every step: {gather})" if n > 1 else "single GPU"),
-            "weights": "seeded random-init, deploy (re-parameterised) form", "in_flight": "2 batches per GPU (two detector handles on two streams)",
+            "weights": "seeded random-init, deploy (re-parameterised) form", "in_flight": "2 batches per GPU (two detector handles on two streams; --engines)",
             "l2": f"per-step working set ~{0.157 * batch:.0f} GB >> 126 MB L2; 4 rotating input batches"}
 
 
@@ -347,7 +347,7 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()  # started during set-up so that nvidia-smi is already streaming when the timed regions begin
-    engs = [Engine(weights, B, IMAGE_SIZE, sparse_heads=not args.dense_heads) for _ in range(2)]
+    engs = [Engine(weights, B, IMAGE_SIZE, sparse_heads=not args.dense_heads) for _ in range(args.engines)]
     eng = engs[0]
     n_rot = 4
     host_imgs = [synth.synthetic_images(B, IMAGE_SIZE, seed=100 * rank + i).pin_memory() for i in range(n_rot)]
@@ -542,6 +542,7 @@ def main():
     ap.add_argument("--dense-heads", action="store_true",
                     help="run the FLAME branch of the heads on the whole feature maps (as the reference graph does) instead of on the "
                          "8x8 windows around the NMS survivors; same predictions, ~20 %% more work")
+    ap.add_argument("--engines", type=int, default=2, help="detector handles per GPU = batches in flight on the device-timed path")
     ap.add_argument("--no-autotune", action="store_true", help="skip the per-layer configuration search (tests)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg of the N=1 line (tests)")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra dense-heads measurement of the N=1 line")

@@ -63,6 +63,8 @@ _SIGS = {
     "vgh_detector_output": (C.c_void_p, [C.c_void_p, C.c_int]),
     "vgh_detector_num_anchors": (C.c_int, [C.c_void_p]),
     "vgh_detector_read_buffer": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
+    "vgh_detector_write_buffer": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
+    "vgh_detector_forward_from": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "vgh_detector_run_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "vgh_detector_submit_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int]),

@@ -923,6 +923,25 @@ extern "C" int vgh_detector_read_buffer(vgh_detector* d, int buf, void* host_dst
   CUDA_OK(cudaMemcpy(host_dst, d->buf_ptr[buf], bytes, cudaMemcpyDeviceToHost));
   return 0;
 }
+extern "C" int vgh_detector_write_buffer(vgh_detector* d, int buf, const void* host_src, size_t bytes) {
+  if (!d || buf < 0 || buf >= (int)d->buf_ptr.size() || !host_src) return fail(1, "bad buffer id");
+  if (bytes > d->buf_bytes[buf]) return fail(1, "write of %zu bytes exceeds buffer (%zu)", bytes, d->buf_bytes[buf]);
+  CUDA_OK(cudaMemcpy(d->buf_ptr[buf], host_src, bytes, cudaMemcpyHostToDevice));
+  return 0;
+}
+// Stage-wise parity aid: runs dense plan ops [first_op, n_dense_ops) over whatever the activation buffers hold (e.g.
+// feature maps written with vgh_detector_write_buffer), then box decode.  first_op == n_dense_ops: decode only.
+extern "C" int vgh_detector_forward_from(vgh_detector* d, int first_op, void* stream) {
+  if (!d || first_op < 1 || first_op > d->n_dense_ops) return fail(1, "first_op must be in [1, n_dense_ops]");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool ml = d->multi_lane;
+  d->multi_lane = false;  // a partial plan has no complete dependency history: run it on one stream
+  int rc = run_ops(d, first_op, d->n_dense_ops, nullptr, s, nullptr);
+  d->multi_lane = ml;
+  if (rc) return rc;
+  if (box_decode_launch(d->lv, d->boxes, d->scores, d->B, d->A, s)) return fail(5, "box decode launch failed");
+  return 0;
+}
 // Synthetic-workload hook (bench / tests): after box decode, overwrite boxes/scores with caller data
 // (random weights never produce detections).  Pass NULLs to disable.
 extern "C" int vgh_detector_set_override(vgh_detector* d, const float* boxes_dev, const float* scores_dev) {

@@ -201,6 +201,23 @@ class Engine:
         t = torch.from_numpy(arr) if fp32 else torch.from_numpy(arr.view(np.int16)).view(torch.bfloat16).float()
         return t.reshape(nb, h, w, c)
 
+    def write_buffer(self, name: str, value: torch.Tensor):
+        """float32 NHWC cpu tensor -> activation buffer `name` (rounded to bf16 unless the buffer is fp32); parity tests."""
+        i = self.plan.buf_names[name]
+        h, w, c, fp32 = self.plan.bufs[i]
+        nb = 1 if i in self.plan.stack_bufs else self.B
+        assert tuple(value.shape) == (nb, h, w, c), (name, tuple(value.shape), (nb, h, w, c))
+        t = value.detach().cpu().contiguous().float()
+        arr = t.numpy() if fp32 else t.to(torch.bfloat16).view(torch.int16).numpy()
+        _lib.check(_lib.lib().vgh_detector_write_buffer(self._h, i, arr.ctypes.data, arr.nbytes), "write_buffer")
+
+    def forward_from(self, first_label: Optional[str]):
+        """Run the dense plan from the op labelled `first_label` (None: box decode only) over the current buffers."""
+        n_dense = self.plan.n_dense_ops if self.plan.n_dense_ops is not None else len(self.plan.ops)
+        first = n_dense if first_label is None else next(i for i, op in enumerate(self.plan.ops) if op.label == first_label)
+        _lib.check(_lib.lib().vgh_detector_forward_from(self._h, first, _lib.stream_ptr()), "forward_from")
+        return self.boxes, self.scores
+
     def autotune(self, iters=3):
         _lib.check(_lib.lib().vgh_detector_autotune(self._h, iters, _lib.stream_ptr()), "autotune")
 

@@ -161,6 +161,11 @@ int vgh_detector_num_anchors(const vgh_detector* d);
 /* Copy an activation buffer to the host (debug / layer-wise parity). */
 int vgh_detector_read_buffer(vgh_detector* d, int buf, void* host_dst, size_t bytes);
 
+/* Stage-wise parity aids (tests): overwrite an activation buffer from the host (same layout as read_buffer: NHWC,
+ * bf16 bits or fp32), and run the dense plan ops [first_op, n_dense_ops) + box decode over the buffers as they are. */
+int vgh_detector_write_buffer(vgh_detector* d, int buf, const void* host_src, size_t bytes);
+int vgh_detector_forward_from(vgh_detector* d, int first_op, void* stream);
+
 /* End to end with HOST buffers (pinned recommended): H2D of images, forward, postprocess, D2H of
  * counts / kept boxes / kept scores / packed params and vertices.  The whole device side replays
  * one CUDA graph.  verts_host capacity = max_heads*5023*3 floats; returns total heads in

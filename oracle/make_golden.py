@@ -16,6 +16,14 @@ Fixtures written (all small, committed):
   letterbox_ref.npz      reference `HeadDetector._transform_image` (detector.py:40-52), one shape
   letterbox_ref_cases.npz  the same on seven more shapes (up/down-scaling, tall, wide, identity);
                          `python oracle/make_golden.py --only-letterbox` rewrites just this file
+  heads_ref.npz          the reference's own `YoloHeadsNDFLHeads` / `YoloHeadsDFLHead` (yolo_head_ndfl_heads.py:117-175,
+                         yolo_head_dfl_head.py:141-186; super_gradients stand-ins in oracle/shims) on seeded feature
+                         maps and seeded weights: raw per-level outputs + decoded boxes / scores / flame[B,A,413]
+  topk_ref.npz           reference `VGGHeadDecodingModule` (yolo_heads.py:44-86) followed by reference `utils.nms`
+  detector_ref.npz       the UNMODIFIED `HeadDetector.__call__` (detector.py:97-102) on a synthetic `vgg_heads_l.trcd`
+                         (oracle/sg_net.py traced; hf_hub_download patched to the local file): boxes, scores, vertices,
+                         plus the stage timing of BASELINE configs[0] -> profiles/r2_reference_cpu_config0.json
+                         (`python oracle/make_golden.py --only-net` rewrites these three)
 """
 import json
 import os
@@ -92,9 +100,138 @@ def letterbox_cases():
     np.savez_compressed(os.path.join(OUT, "letterbox_ref_cases.npz"), **out)
 
 
+HEADS_SEED, HEADS_S, HEADS_B = 5, 128, 2
+DETECTOR_SEED, DETECTOR_CLS_BIAS = 1, 1.5
+
+
+def heads_feats(seed=HEADS_SEED, S=HEADS_S, B=HEADS_B):
+    """Seeded neck outputs p3/p4/p5, bf16-representable (the CUDA path stores activations in bf16)."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    return [(torch.randn(B, c, S // st, S // st, generator=g) * 1.5).clamp_min(0).to(torch.bfloat16).float() for c, st in ((96, 8), (192, 16), (384, 32))]
+
+
+def heads_cases():
+    """The reference's head + decode classes on seeded weights (oracle/sg_net.py names == the reference's names)."""
+    from oracle import ref_heads, sg_net
+
+    ns = ref_heads.load()
+    ref = ref_heads.build_heads(ns)
+    sd = {k[len("heads."):]: v for k, v in sg_net.build(HEADS_SEED).state_dict().items() if k.startswith("heads.")}
+    ref.load_state_dict(sd, strict=True)
+    feats = heads_feats()
+    out = {"seed": np.array(HEADS_SEED), "S": np.array(HEADS_S)}
+    with torch.no_grad():
+        dec, _ = ref(feats)
+        for l, f in enumerate(feats, start=1):
+            h = getattr(ref, f"head{l}")
+            reg, cls, flame = h(f)                                   # yolo_head_dfl_head.py:141-186
+            pose = h.pose_stem(h.stem(f))
+            out[f"reg{l}"], out[f"cls{l}"], out[f"flame{l}"] = reg.numpy(), cls.numpy(), flame.numpy()
+            for tw, attr in (("shape", "flame_shape_pred"), ("expr", "flame_expression_pred"), ("rot", "flame_rotation_pred"),
+                             ("jaw", "flame_jaw_pred"), ("transl", "flame_translation_pred"), ("scale", "flame_scale_pred")):
+                out[f"{tw}{l}"] = getattr(h, attr)(pose).numpy()     # pre-activation tower outputs
+    out["boxes"], out["scores"], out["flame"] = dec.boxes_xyxy.numpy(), dec.scores.numpy(), dec.flame_params.numpy()
+    np.savez_compressed(os.path.join(OUT, "heads_ref.npz"), **out)
+    print("heads_ref: anchors", out["boxes"].shape, "scale range", out["flame"][..., 412].min(), out["flame"][..., 412].max())
+
+    # top-k decoding module + utils.nms, per image (utils.nms handles the first image only)
+    from head_detector.utils import nms as ref_nms
+
+    dm = ns.VGGHeadDecodingModule(1000)
+    B, A = 2, 2100
+    boxes = torch.stack([clustered_anchors(A, 20, 14, 40 + b, size=320.0, bg_hi=0.8)[0] for b in range(B)])
+    scores = torch.stack([clustered_anchors(A, 20, 14, 40 + b, size=320.0, bg_hi=0.8)[1] for b in range(B)])
+    tag = torch.zeros(B, A, 413)
+    tag[..., 0] = torch.arange(A)
+    preds = type("P", (), {"boxes_xyxy": boxes, "scores": scores[..., None], "flame_params": tag})()
+    tb, ts, tf = dm((preds, None))
+    cases = {"boxes": boxes.numpy(), "scores": scores.numpy(), "topk_ids": tf[..., 0].long().numpy()}
+    for b in range(B):
+        kb, ks, kf = ref_nms(tb[b:b + 1], ts[b:b + 1], tf[b:b + 1], confidence_threshold=0.5)
+        cases[f"keep{b}"] = kf[:, 0].long().numpy()
+        print("topk_ref image", b, "candidates", int((scores[b] >= 0.5).sum()), "kept", len(ks))
+    np.savez_compressed(os.path.join(OUT, "topk_ref.npz"), **cases)
+
+
+def detector_image(seed=DETECTOR_SEED):
+    """Non-square seeded frame with smooth structure (letterboxed by the detector: 480x640 -> pad (0, 80))."""
+    rng = np.random.default_rng(seed)
+    low = rng.integers(0, 256, (15, 20, 3), dtype=np.uint8)
+    import cv2
+    return cv2.resize(low, (640, 480), interpolation=cv2.INTER_CUBIC)
+
+
+def detector_net(seed=DETECTOR_SEED):
+    """Synthetic detector whose class logits are shifted so that a few hundred anchors pass the 0.5 threshold."""
+    from oracle import sg_net
+
+    net = sg_net.build(seed)
+    with torch.no_grad():
+        for l in (1, 2, 3):
+            getattr(net.heads, f"head{l}").cls_pred.bias.fill_(DETECTOR_CLS_BIAS)
+    return net
+
+
+def detector_case():
+    """BASELINE configs[0]: the unmodified reference HeadDetector on torch-CPU with a synthetic vgg_heads_l.trcd."""
+    import tempfile
+    import time
+
+    import head_detector.detector as refdet
+    from oracle import sg_net
+
+    tmp = tempfile.mkdtemp()
+    path = sg_net.trace_to(os.path.join(tmp, "vgg_heads_l.trcd"), detector_net(), 640)
+    refdet.hf_hub_download = lambda repo, name: path          # the one patch: no network
+    det = refdet.HeadDetector()                                # reference constructor, torch.jit.load of the blob
+    img = detector_image()
+    res = det(img, confidence_threshold=0.5)                   # reference __call__
+    n = len(res.heads)
+    print("detector_ref: heads", n, "first bbox", tuple(res.heads[0].bbox) if n else None)
+    keep_v = min(n, 12)
+    np.savez_compressed(
+        os.path.join(OUT, "detector_ref.npz"), seed=np.array(DETECTOR_SEED), cls_bias=np.array(DETECTOR_CLS_BIAS),
+        bbox_xywh=np.array([[int(v) for v in h.bbox] for h in res.heads]).reshape(n, 4), scores=np.array([float(h.score) for h in res.heads]),
+        vertices_3d=np.stack([h.vertices_3d for h in res.heads[:keep_v]]) if n else np.zeros((0, 5023, 3), np.float32),
+        vertex_mean=np.array([h.vertices_3d.mean(0) for h in res.heads]).reshape(n, 3),
+        rpy=np.array([[h.head_pose.roll, h.head_pose.pitch, h.head_pose.yaw] for h in res.heads]).reshape(n, 3),
+        params=np.stack([torch.cat([h.flame_params.shape, h.flame_params.expression, h.flame_params.jaw, h.flame_params.rotation,
+                                    h.flame_params.translation, h.flame_params.scale], dim=1)[0].numpy() for h in res.heads]) if n else np.zeros((0, 413), np.float32))
+    # stage split of config 0 (SURVEY 8d): model / nms / flame+parse / result object, torch-CPU, this container's cores
+    x, cache = det._preprocess(img)
+    reps, t = 3, {}
+    with torch.no_grad():
+        det._process(x)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            out = det._process(x)
+        t["model_ms"] = 1e3 * (time.perf_counter() - t0) / reps
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            kept = refdet.nms(*out, confidence_threshold=0.5)
+        t["nms_ms"] = 1e3 * (time.perf_counter() - t0) / reps
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            det._parse_predictions(*kept, cache)
+        t["flame_parse_ms"] = 1e3 * (time.perf_counter() - t0) / reps
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            det(img)
+        t["call_ms"] = 1e3 * (time.perf_counter() - t0) / reps
+    t.update(heads=n, threads=torch.get_num_threads(), cores=os.cpu_count(),
+             what="unmodified reference HeadDetector.__call__ (detector.py:97-102), torch-CPU fp32, synthetic vgg_heads_l.trcd traced from oracle/sg_net.py, 480x640 frame")
+    os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
+    json.dump(t, open(os.path.join(ROOT, "profiles", "r2_reference_cpu_config0.json"), "w"), indent=1)
+    print("config 0 timing", t)
+
+
 def main():
     if "--only-letterbox" in sys.argv:
         letterbox_cases()
+        return
+    if "--only-net" in sys.argv:
+        heads_cases()
+        detector_case()
         return
     os.makedirs(OUT, exist_ok=True)
     from head_detector.flame import FLAMELayer, reproject_spatial_vertices  # the reference, unmodified
@@ -161,6 +298,8 @@ def main():
     np.savez_compressed(os.path.join(OUT, "letterbox_ref.npz"), sha1=np.frombuffer(hashlib.sha1(u8.tobytes()).digest(), dtype=np.uint8),
                         pad=np.array(pad), scale=np.array(scale), probe=u8[::37, ::41].copy(), seed=np.array(17), shape=np.array(src.shape))
     letterbox_cases()
+    heads_cases()
+    detector_case()
     print("golden fixtures written to", OUT)
 
 

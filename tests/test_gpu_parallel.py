@@ -275,7 +275,7 @@ def _bench_worker(rank, world, q, steps, gather):
     lines = []
     for k in steps:
         args = argparse.Namespace(gpus=world, steps=k, warmup=5, impl="ours", per_gpu_batch=2, gather=gather, dense_heads=False,
-                                  no_autotune=True, no_cpu_baseline=True, no_extras=True, keep_process_group=True)
+                                  no_autotune=True, no_cpu_baseline=True, no_extras=True, keep_process_group=True, engines=2)
         line = bench.run_ours(args, rank, world, rank)
         if rank == 0:
             lines.append({k2: line[k2] for k2 in ("value", "n_gpus", "steps", "gather", "heads_per_step_per_gpu")} | {"e2e": line["e2e"]["value"], "parity": line["parity"]})
