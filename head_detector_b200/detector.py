@@ -4,32 +4,42 @@
     HeadDetector(model="vgg_heads_l", image_size=640)(image, confidence_threshold=0.5)
         -> PredictionResult with .heads[i].bbox / .score / .flame_params / .vertices_3d / .head_pose
 
-Differences that are extensions, not changes: `weights=` (a deploy-form weight dict or a path to a
-torch-saved one; the HF download of detector.py:25-30 is impossible offline), `batch_size=` and
-`detect_batch()` (batched semantics of yolo_heads_post_prediction_callback.py:55-97), and
-`device_letterbox=` (default True: `_transform_image` runs as one CUDA kernel for the whole batch,
-bit-exact with the cv2 calls of detector.py:47-50; False keeps the reference's host cv2 path) and
-`sparse_heads=` (default True: the FLAME branch of the detection heads is evaluated after NMS on 8x8
-windows around the surviving anchors instead of on the whole feature maps - same heads, same numbers)."""
+The reference's seam is kept name for name: `_read_model(model)`, `_convert_image`, `_transform_image`, `_preprocess`,
+`_process`, `_postprocess(predictions, cache, confidence_threshold)`, `_parse_predictions(bboxes_xyxy, scores,
+flame_params, cache)`, `__call__` (detector.py:25-102), so a subclass written against the reference still fits.
+
+Extensions (keyword-only constructor arguments, extra methods): `weights=` - path to the TorchScript blob
+`vgg_heads_l.trcd` the reference downloads (the HF download itself is impossible offline), a state_dict checkpoint, a
+deploy-form dict, or "synthetic" (`weights.py`; nothing is substituted silently); `batch_size=`, `predict_batch()` and
+`detect_batch()` (batched semantics of yolo_heads_post_prediction_callback.py:55-97); `device_letterbox=` (default True:
+`_transform_image` runs as one CUDA kernel for the whole batch, bit-exact with the cv2 calls of detector.py:47-50; False
+keeps the reference's host cv2 path); `sparse_heads=` (default True: the FLAME branch of the detection heads is
+evaluated after NMS on 8x8 windows around the surviving anchors instead of on the whole feature maps - same heads, same
+numbers); `parity=` (fp32-class conv arithmetic for end-to-end comparisons with the reference)."""
 import os
-import warnings
 from typing import Any, Dict, List, Optional, Tuple, Union
 
 import numpy as np
 import torch
 
-from . import arch
+from . import arch  # noqa: F401
 from .detection_result import PredictionResult
 from .engine import Engine
 from .flame import FLAMELayer
 from .head_info import FLAME_CONSTS, Bbox, FlameParams, HeadMetadata
 from .preprocess import letterbox_batch, letterbox_geometry
 from .utils import rpy_from_rotations
+from .weights import resolve as resolve_weights
 
 
 class HeadDetector:
-    def __init__(self, model: str = "vgg_heads_l", image_size: int = 640, weights: Union[None, str, Dict[str, torch.Tensor]] = None,
-                 batch_size: int = 1, keep_top_k: int = 100, device_letterbox: bool = True, sparse_heads: bool = True):
+    def __init__(self, model: str = "vgg_heads_l", image_size: int = 640, *, weights: Union[None, str, Dict[str, torch.Tensor]] = None,
+                 batch_size: int = 1, keep_top_k: int = 100, device_letterbox: bool = True, sparse_heads: bool = True, parity: bool = False):
+        """`model`, `image_size`: the reference's arguments (detector.py:19).  Keyword-only extensions: `weights` - path to
+        `vgg_heads_l.trcd` (the TorchScript blob the reference downloads) / a state_dict checkpoint / a deploy-form dict /
+        the literal "synthetic" (default: $VGGHEADS_B200_WEIGHTS; there is no silent fallback to random weights);
+        `batch_size` for `predict_batch`; `parity=True` runs the conv network in the fp32-class split-bf16 mode
+        (slow; dense heads) for end-to-end comparisons with the reference's fp32 path."""
         if not torch.cuda.is_available():
             raise RuntimeError("head_detector_b200.HeadDetector needs a CUDA device (sm_100a); there is no CPU fallback")
         self._image_size = image_size
@@ -38,21 +48,18 @@ class HeadDetector:
         self._batch = batch_size
         self._keep_top_k = keep_top_k
         self._device_letterbox = device_letterbox
-        self._sparse_heads = sparse_heads   # FLAME branch of the heads on the NMS survivors only (same predictions)
-        self.model = self._read_model(model, weights)
+        self._sparse_heads = sparse_heads and not parity   # FLAME branch of the heads on the NMS survivors only (same predictions)
+        self._parity = parity
+        self._weights = weights if weights is not None else os.environ.get("VGGHEADS_B200_WEIGHTS")
+        self.model = self._read_model(model)
 
-    def _read_model(self, model: str, weights=None) -> Engine:
+    def _read_model(self, model: str) -> Engine:
+        """detector.py:25-30: where the reference `torch.jit.load`s the downloaded blob, this builds the engine from the
+        same blob (weights.load_checkpoint: TorchScript -> state_dict -> re-parameterised, packed weights)."""
         if model != "vgg_heads_l":
             raise ValueError(f"unknown model {model!r}; only 'vgg_heads_l' (YoloHeads_L) is built")
-        if weights is None:
-            weights = os.environ.get("VGGHEADS_B200_WEIGHTS")
-        if isinstance(weights, str):
-            weights = torch.load(weights, map_location="cpu")
-        if weights is None:
-            warnings.warn("no weights given and the released vgg_heads_l checkpoint is unreachable offline: "
-                          "using seeded random-init weights (architecture and cost are exact, detections are not meaningful)")
-            weights = arch.synthetic_weights(0)
-        return Engine(weights, self._batch, self._image_size, self._keep_top_k, self._flame, sparse_heads=self._sparse_heads)
+        w = resolve_weights(self._weights, model)
+        return Engine(w, self._batch, self._image_size, self._keep_top_k, self._flame, sparse_heads=self._sparse_heads, parity=self._parity)
 
     # -- host-side pre-processing, same arithmetic as detector.py:32-56
     def _convert_image(self, image) -> np.ndarray:
@@ -78,6 +85,45 @@ class HeadDetector:
             image = cv2.copyMakeBorder(image, pad_h // 2, pad_h - pad_h // 2, pad_w // 2, pad_w - pad_w // 2,
                                        cv2.BORDER_CONSTANT, value=127)
         return np.ascontiguousarray(image[..., :3], dtype=np.uint8), (pad_w // 2, pad_h // 2), scale
+
+    # -- the reference's seam (detector.py:54-59,61-95), same names / arguments / return types
+    def _preprocess(self, image: np.ndarray) -> Tuple[torch.Tensor, Dict[str, Any]]:
+        """detector.py:54-56.  The model input here is the letterboxed uint8 frame [batch,S,S,3] on the device (the /255
+        of detector.py:51 is folded into the stem weights)."""
+        batch, xf, caches = self._prepare_batch([image])
+        cache = dict(caches[0])
+        cache["_xform"] = xf
+        return batch, cache
+
+    def _process(self, image: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
+        """detector.py:58-59 `self.model(image)` -> (boxes [B,A,4], scores [B,A,1], flame [B,A,413]).  With sparse heads the
+        dense 413-wide tensor is never built (its rows are assembled for the NMS survivors only): flame is None."""
+        boxes, scores = self.model.forward(image.to(self._device))
+        return boxes, scores[..., None], (None if self.model.sparse_heads else self.model.dense_flame())
+
+    def _postprocess(self, predictions, cache: Dict[str, Any], confidence_threshold: float) -> List[HeadMetadata]:
+        """detector.py:92-95: `nms` (first image, utils.py:159-194) + `_parse_predictions`.  Select / top-k / NMS, the survivors'
+        413-float rows and the FLAME decode all run on the device in `Engine.postprocess`; the decoded vertices ride along
+        in the cache so that `_parse_predictions` does not decode a second time."""
+        eng = self.model
+        eng.postprocess(confidence_threshold, 0.5, 1000, cache.get("_xform"))
+        n = int(eng.head_offsets[1])
+        cache = dict(cache)
+        cache["_decoded"] = (eng.head_verts(n), eng.head_rot(n))
+        return self._parse_predictions(eng.keep_boxes[0, :n], eng.keep_scores[0, :n], eng.head_params(n), cache)
+
+    def _parse_predictions(self, bboxes_xyxy: torch.Tensor, scores: torch.Tensor, flame_params: torch.Tensor, cache: Dict[str, Any]) -> List[HeadMetadata]:
+        """detector.py:61-90, reference signature: kept boxes [n,4], scores [n], flame rows [n,413] + {"padding", "scale"}."""
+        n = int(flame_params.shape[0])
+        pad, scale = cache["padding"], cache["scale"]
+        if "_decoded" in cache:
+            verts, rots = cache["_decoded"]
+        else:   # called on its own: decode here (vertices un-padded / un-scaled by the kernel, detector.py:67-69)
+            xf = torch.tensor([[pad[0], pad[1], scale]], dtype=torch.float32).expand(max(n, 1), 3)[:n]
+            _, rots, verts = self._flame.decode(flame_params, xf, live=(300, 100)) if n else (None, torch.zeros(0, 3, 3), torch.zeros(0, 5023, 3))
+        out = {"offsets": torch.tensor([0, n]), "keep_boxes": bboxes_xyxy.reshape(1, n, 4), "keep_scores": scores.reshape(1, n),
+               "vertices": verts, "params": flame_params, "rotations": rots}
+        return self._parse_batch(out, [cache])[0]
 
     # -- batched device path
     def detect_batch(self, images_u8: torch.Tensor, confidence_threshold: float = 0.5, img_xform: Optional[torch.Tensor] = None):
@@ -133,13 +179,6 @@ class HeadDetector:
                                                  flame_params=fp, vertices_3d=verts[i], head_pose=poses[i]))
         return heads
 
-    def _parse_predictions(self, out: Dict[str, torch.Tensor], img: int, cache: Dict[str, Any]) -> List[HeadMetadata]:
-        """detector.py:61-90 for image `img` of the batch."""
-        lo, hi = int(out["offsets"][img]), int(out["offsets"][img + 1])
-        one = {"offsets": torch.tensor([0, hi - lo]), "keep_boxes": out["keep_boxes"][img:img + 1], "keep_scores": out["keep_scores"][img:img + 1],
-               "vertices": out["vertices"][lo:hi], "params": out["params"][lo:hi], "rotations": out["rotations"][lo:hi]}
-        return self._parse_batch(one, [cache])[0]
-
     def predict_batch(self, images: List[Any], confidence_threshold: float = 0.5) -> List[PredictionResult]:
         """Batched `__call__` (extension; semantics of yolo_heads_post_prediction_callback.py:55-97: every image
         independently).  `len(images)` must not exceed the `batch_size` the detector was built with; the
@@ -173,8 +212,9 @@ class HeadDetector:
         return batch, xf, caches
 
     def __call__(self, image, confidence_threshold: float = 0.5) -> PredictionResult:
-        original = self._convert_image(image)
-        batch, xf, caches = self._prepare_batch([original])
-        out = self.detect_batch(batch, confidence_threshold, xf)
-        heads = self._parse_predictions(out, 0, caches[0])
-        return PredictionResult(original_image=original, heads=heads)
+        """detector.py:97-102, step for step."""
+        original_image = self._convert_image(image)
+        image, cache = self._preprocess(original_image)
+        predictions = self._process(image)
+        heads = self._postprocess(predictions, cache, confidence_threshold)
+        return PredictionResult(original_image=original_image, heads=heads)
