@@ -41,7 +41,7 @@ class NetDesc(C.Structure):
         ("weights_host", C.c_void_p), ("n_weights", C.c_int64),
         ("bias_host", C.c_void_p), ("n_bias", C.c_int64),
         ("reg_buf", C.c_int32 * 3), ("flame_buf", C.c_int32 * 3),
-        ("keep_k", C.c_int32), ("n_dense_ops", C.c_int32),
+        ("keep_k", C.c_int32), ("n_dense_ops", C.c_int32), ("split", C.c_int32),
     ]
 
 
@@ -55,6 +55,8 @@ _SIGS = {
     "vgh_select_nms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vgh_letterbox": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vgh_pncc_render": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vgh_head_bbox": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "vgh_detector_create": (C.c_int, [C.POINTER(NetDesc), C.c_void_p, C.POINTER(C.c_void_p)]),
     "vgh_detector_destroy": (None, [C.c_void_p]),
     "vgh_detector_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -86,6 +86,7 @@ class Plan:
         self.stack_bufs: set = set()  # buffers that are ONE stacked image [H,W,C] (survivor patches), not [B,H,W,C]
         self.n_dense_ops: Optional[int] = None  # sparse heads: ops [0, n_dense_ops) run before select/NMS, the rest after
         self.patch_cap = 0  # sparse heads: patch capacity per level (batch * keep_top_k)
+        self.split = False  # parity mode (split_plan): bf16 buffers hold six planes [h|m|h|m|h|l] per 32-channel granule
 
     # -- helpers
     def buf(self, name, res, C, fp32=0):
@@ -273,6 +274,42 @@ def build_plan(image_size: int = 640, sparse_heads: Optional[Tuple[int, int]] = 
     return P
 
 
+SPLIT_PLANES = 6
+# weight term multiplying activation plane q of [x_h | x_m | x_h | x_m | x_h | x_l]:  0 = w_h, 1 = w_m, 2 = w_l
+SPLIT_WEIGHT_TERM = (0, 0, 1, 1, 2, 0)
+
+
+def split_plan(P: Plan) -> Plan:
+    """Parity mode (include/vggheads_b200.h `vgh_net_desc.split`): the same dense plan over activations stored as three
+    bf16 terms.  Logical channel c of a bf16 buffer lives at 192*(c//32) + 32*plane + c%32; channel offsets / widths of
+    every op are scaled by 6; fp32 buffers (raw head outputs) are untouched.  Pure bookkeeping - the arithmetic change
+    is in the epilogue (three-term split store) and in `pack` (weight terms along K)."""
+    assert P.n_dense_ops is None, "parity mode runs the dense-heads plan"
+    P.split = True
+    is_bf16 = [not fp32 for (_, _, _, fp32) in P.bufs]
+    P.bufs = [(h, w, c * SPLIT_PLANES if not fp32 else c, fp32) for (h, w, c, fp32) in P.bufs]
+    for op in P.ops:
+        if op.kind == _lib.OP_STEM:
+            continue
+        if op.kind == _lib.OP_SPP:   # the kernel works in logical channels
+            continue
+        assert op.src[1] % 32 == 0 and op.src[2] % 32 == 0 and op.dst[1] % 32 == 0, op.label
+        op.src = (op.src[0], op.src[1] * SPLIT_PLANES, op.src[2] * SPLIT_PLANES)
+        if is_bf16[op.dst[0]]:
+            op.dst = (op.dst[0], op.dst[1] * SPLIT_PLANES)
+        if op.res is not None:
+            op.res = (op.res[0], op.res[1] * SPLIT_PLANES, op.res[2])
+    return P
+
+
+def split_terms(w: torch.Tensor):
+    """fp32 -> (h, m, l) bf16-representable fp32 tensors with h + m + l == w (exactly, in fp32)."""
+    h = w.to(torch.bfloat16).float()
+    m = (w - h).to(torch.bfloat16).float()
+    l = (w - h - m).to(torch.bfloat16).float()
+    return h, m, l
+
+
 def _auto_block_n(cout: int, up: int, up_cout: int) -> int:
     lim = up_cout if up else cout
     if lim <= 256:
@@ -299,7 +336,7 @@ def pack(plan: Plan, w: Dict[str, torch.Tensor]) -> PackedNet:
         if op.kind != _lib.OP_CONV:
             meta.append({})
             continue
-        cin, taps = op.src[2], op.k * op.k
+        cin, taps = op.src[2] // (SPLIT_PLANES if plan.split else 1), op.k * op.k   # logical channels per tap
         block_n = _auto_block_n(op.cout, op.up, op.up_cout)
         n_pad = (op.cout + block_n - 1) // block_n * block_n
         if not op.up:  # operand-swapped kernel: G channel groups of gw <= 128, each fetched as a 128-row box
@@ -329,6 +366,11 @@ def pack(plan: Plan, w: Dict[str, torch.Tensor]) -> PackedNet:
                 M[p.row:p.row + p.cout, :, phys:phys + n] = wk[:, :, log:log + n]
             bvec[p.row:p.row + p.cout] = bt
         alpha = float(w[op.res[2]]) if op.res is not None else 0.0
+        if plan.split:   # K columns per 32-channel granule: [w_h | w_h | w_m | w_m | w_l | w_h] against [x_h | x_m | x_h | x_m | x_h | x_l]
+            terms = split_terms(M)
+            G = M.reshape(n_pad, taps, cin // 32, 1, 32)
+            M = torch.cat([terms[t].reshape_as(G) for t in SPLIT_WEIGHT_TERM], dim=3).reshape(n_pad, taps, cin * SPLIT_PLANES)
+            cin = cin * SPLIT_PLANES
         chunk = M.reshape(-1).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
         pad = (-chunk.size) % 64  # keep every TMA base address 128-byte aligned
         if pad:

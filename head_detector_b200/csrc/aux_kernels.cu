@@ -18,7 +18,7 @@ namespace vgh {
 // the tensor cores as a 1x1 conv with Cin = 32 whose weights carry the /255 of detector.py:51.
 // uint8 -> bf16 is exact.
 __global__ void __launch_bounds__(256) stem_pack_kernel(const uint8_t* __restrict__ img, __nv_bfloat16* __restrict__ out,
-                                                        int B, int S) {
+                                                        int B, int S, int split) {
   // thread = one output pixel: its 3x3x3 window is three runs of 9 consecutive bytes (one per image row)
   const int Ho = S >> 1;
   const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) stem_pack_kernel(const uint8_t* __restric
       x[ky * 9 + j] = ok ? static_cast<float>(__ldg(p + j)) : 0.f;
     }
   }
-  uint4* op = reinterpret_cast<uint4*>(out + pix * 32);
+  uint4* op = reinterpret_cast<uint4*>(out + pix * (split ? 192 : 32));
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     uint32_t w[4];
@@ -51,13 +51,18 @@ __global__ void __launch_bounds__(256) stem_pack_kernel(const uint8_t* __restric
       __nv_bfloat162 h = __floats2bfloat162_rn(x[u * 8 + 2 * i], x[u * 8 + 2 * i + 1]);
       w[i] = *reinterpret_cast<uint32_t*>(&h);
     }
-    op[u] = make_uint4(w[0], w[1], w[2], w[3]);
+    const uint4 v = make_uint4(w[0], w[1], w[2], w[3]);
+    op[u] = v;
+    if (split) {  // planes [h|m|h|m|h|l] of 32 channels (4 uint4) each; m and l stay zero (the buffer is zero-initialised)
+      op[8 + u] = v;
+      op[16 + u] = v;
+    }
   }
 }
 
-int stem_pack_launch(const uint8_t* img, __nv_bfloat16* out, int B, int S, cudaStream_t stream) {
+int stem_pack_launch(const uint8_t* img, __nv_bfloat16* out, int B, int S, int split, cudaStream_t stream) {
   const long long total = static_cast<long long>(B) * (S / 2) * (S / 2);
-  stem_pack_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, stream>>>(img, out, B, S);
+  stem_pack_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, stream>>>(img, out, B, S, split);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
@@ -129,6 +134,54 @@ int spp_pool_launch(__nv_bfloat16* buf, int B, int H, int W, int C, cudaStream_t
     configured = smem;
   }
   spp_pool_kernel<<<B * (C / CH), 256, smem, stream>>>(buf, B, H, W, C, CH);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+// Parity mode: activations are split bf16 terms, six planes [h|m|h|m|h|l] per 32-channel granule.  One thread per
+// (image, pixel, logical channel): y = (l + m) + h is exact in fp32, the three pools are plain window maxima over y
+// (small maps, parity runs only - no attempt at speed), results are re-split and written to slices 1..3.
+__device__ __forceinline__ float split_load(const __nv_bfloat16* g) {
+  return (__bfloat162float(g[160]) + __bfloat162float(g[32])) + __bfloat162float(g[0]);
+}
+__device__ __forceinline__ void split_store(__nv_bfloat16* g, float y) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(y);
+  y -= __bfloat162float(h);
+  const __nv_bfloat16 m = __float2bfloat16_rn(y);
+  y -= __bfloat162float(m);
+  g[0] = h; g[64] = h; g[128] = h;
+  g[32] = m; g[96] = m;
+  g[160] = __float2bfloat16_rn(y);
+}
+__global__ void __launch_bounds__(256) spp_pool_split_kernel(__nv_bfloat16* __restrict__ buf, int B, int H, int W, int C) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(B) * H * W * C) return;
+  const int c = static_cast<int>(idx % C);
+  const int x = static_cast<int>((idx / C) % W), y = static_cast<int>((idx / C / W) % H), b = static_cast<int>(idx / C / W / H);
+  const size_t CT = static_cast<size_t>(4 * C) * 6;
+  const __nv_bfloat16* img = buf + static_cast<size_t>(b) * H * W * CT;
+  const int goff = 192 * (c >> 5) + (c & 31);
+  float m5 = -INFINITY, m9 = -INFINITY, m13 = -INFINITY;
+  for (int dy = -6; dy <= 6; ++dy) {
+    const int yy = y + dy;
+    if (yy < 0 || yy >= H) continue;
+    for (int dx = -6; dx <= 6; ++dx) {
+      const int xx = x + dx;
+      if (xx < 0 || xx >= W) continue;
+      const float v = split_load(img + (static_cast<size_t>(yy) * W + xx) * CT + goff);
+      m13 = fmaxf(m13, v);
+      if (abs(dy) <= 4 && abs(dx) <= 4) m9 = fmaxf(m9, v);
+      if (abs(dy) <= 2 && abs(dx) <= 2) m5 = fmaxf(m5, v);
+    }
+  }
+  __nv_bfloat16* o = buf + (static_cast<size_t>(b) * H * W + static_cast<size_t>(y) * W + x) * CT + goff;
+  split_store(o + 6 * C, m5);
+  split_store(o + 12 * C, m9);
+  split_store(o + 18 * C, m13);
+}
+int spp_pool_split_launch(__nv_bfloat16* buf, int B, int H, int W, int C, cudaStream_t stream) {
+  if (C % 32) return 1;
+  const long long total = static_cast<long long>(B) * H * W * C;
+  spp_pool_split_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, stream>>>(buf, B, H, W, C);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

@@ -23,8 +23,11 @@ struct DecodeLevels {
 
 constexpr int kPatch = 8, kPatchC = 3;  // survivor patch size / offset of the anchor inside it (arch.py PATCH, PATCH_C)
 
-int stem_pack_launch(const uint8_t* img, __nv_bfloat16* out, int B, int S, cudaStream_t stream);
+// split != 0 (parity mode): the 32-wide row goes to planes 0, 2, 4 of a 192-wide granule (uint8 values are exact in bf16: m = l = 0)
+int stem_pack_launch(const uint8_t* img, __nv_bfloat16* out, int B, int S, int split, cudaStream_t stream);
 int spp_pool_launch(__nv_bfloat16* buf, int B, int H, int W, int C, cudaStream_t stream);
+// parity mode: the same pools on split activations (C logical channels = 6C physical per slice): max over y = h + m + l
+int spp_pool_split_launch(__nv_bfloat16* buf, int B, int H, int W, int C, cudaStream_t stream);
 int box_decode_launch(const DecodeLevels& lv, float* boxes, float* scores, int B, int A, cudaStream_t stream);
 int flame_dense_launch(const DecodeLevels& lv, float* out, int B, int A, cudaStream_t stream);
 int head_offsets_launch(const int* keep_cnt, int B, int* offsets, int* total, cudaStream_t stream);

@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         const size_t res_off =
             ((static_cast<size_t>(b_img) * p.Ho + oh) * p.Wo + ow) * p.res_cstride + p.res_coff + n0;
         const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + acc * acc_cols + ti * p.block_n;
-        const bool use_res = (p.res != nullptr) && row_ok;
+        const bool use_res = (p.res != nullptr) && row_ok && !p.split;
         // chunks of this warp: chunk0, chunk0+2, ...; handled four at a time so that the residual
         // loads of a whole group are in flight before the first one is consumed
         for (int cg = chunk0; cg < n_chunks; cg += 8) {
@@ -258,6 +258,50 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
             if (p.relu) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+            }
+            if (p.split) {
+              // Parity mode (fp32-class arithmetic on the bf16 tensor pipe): an activation y is stored as three bf16 terms
+              // h = bf16(y), m = bf16(y - h), l = bf16(y - h - m) (y == h + m + l exactly), laid out per 32-channel granule
+              // as six planes [h|m|h|m|h|l]; the consumer's weights are packed [w_h|w_h|w_m|w_m|w_l|w_h] along K, so its
+              // MMA accumulates x_h w_h + x_m w_h + x_h w_m + x_m w_m + x_h w_l + x_l w_h in fp32.
+              const int nl = (n0 - n_shift) + c * 16;  // logical channel inside the producer's slice
+              if (p.res != nullptr) {
+                const int nr = n0 + c * 16;
+                const __nv_bfloat16* rp = p.res + ((static_cast<size_t>(b_img) * p.Ho + oh) * p.Wo + ow) * p.res_cstride + p.res_coff +
+                                          192 * (nr >> 5) + (nr & 31);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const float rh = __bfloat162float(rp[i]), rm = __bfloat162float(rp[32 + i]), rl = __bfloat162float(rp[160 + i]);
+                  f[i] = fmaf(p.res_alpha, (rl + rm) + rh, f[i]);
+                }
+              }
+              __nv_bfloat16* op = static_cast<__nv_bfloat16*>(p.out) + out_pix * p.out_cstride + p.out_coff + 192 * (nl >> 5) + (nl & 31);
+              uint32_t wh[8], wm[8], wl[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float y0 = f[2 * i], y1 = f[2 * i + 1];
+                const __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1);
+                y0 -= __bfloat162float(h.x);
+                y1 -= __bfloat162float(h.y);
+                const __nv_bfloat162 m = __floats2bfloat162_rn(y0, y1);
+                y0 -= __bfloat162float(m.x);
+                y1 -= __bfloat162float(m.y);
+                const __nv_bfloat162 l = __floats2bfloat162_rn(y0, y1);
+                wh[i] = *reinterpret_cast<const uint32_t*>(&h);
+                wm[i] = *reinterpret_cast<const uint32_t*>(&m);
+                wl[i] = *reinterpret_cast<const uint32_t*>(&l);
+              }
+              const uint4 h0 = make_uint4(wh[0], wh[1], wh[2], wh[3]), h1 = make_uint4(wh[4], wh[5], wh[6], wh[7]);
+              const uint4 m0 = make_uint4(wm[0], wm[1], wm[2], wm[3]), m1 = make_uint4(wm[4], wm[5], wm[6], wm[7]);
+              uint4* o4 = reinterpret_cast<uint4*>(op);  // planes are 32 channels = 4 uint4 apart
+              o4[0] = h0;  o4[1] = h1;
+              o4[4] = m0;  o4[5] = m1;
+              o4[8] = h0;  o4[9] = h1;
+              o4[12] = m0; o4[13] = m1;
+              o4[16] = h0; o4[17] = h1;
+              o4[20] = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+              o4[21] = make_uint4(wl[4], wl[5], wl[6], wl[7]);
+              continue;
             }
             if (p.res != nullptr) {
               const uint32_t w[8] = {rq[g][0].x, rq[g][0].y, rq[g][0].z, rq[g][0].w, rq[g][1].x, rq[g][1].y, rq[g][1].z, rq[g][1].w};

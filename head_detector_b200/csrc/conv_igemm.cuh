@@ -48,6 +48,7 @@ struct ConvLaunch {
                                  // and reused by the three row taps (xslots = pixel-tile ring depth; `stages` = weight ring)
   int cluster;                   // swapped kernel: 1, or 2 = CTA pairs share every weight k-block (each fetches half, TMA multicast)
   int acc_stages, n_tiles, num_items;  // TMEM accumulator stages (1|2), N tiles, work items (persistent CTAs)
+  int split;                     // normal kernel, parity mode: store y as bf16 terms h|m|l in six planes per 32-channel granule
 };
 
 // Host side (conv_igemm.cu)

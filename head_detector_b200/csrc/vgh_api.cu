@@ -15,6 +15,7 @@
 #include "flame_decode.cuh"
 #include "gather.cuh"
 #include "letterbox.cuh"
+#include "mesh_kernels.cuh"
 #include "select_nms.cuh"
 
 using namespace vgh;
@@ -87,6 +88,25 @@ extern "C" int vgh_letterbox(const uint8_t* src_dev, const int64_t* offsets, con
                           static_cast<cudaStream_t>(stream), g_err, sizeof(g_err));
 }
 
+// ------------------------------------------------------------------------------------------ mesh consumers
+extern "C" int vgh_pncc_render(const float* verts_dev, int n, const int32_t* tris_dev, int ntri, const float* colors_dev, int H, int W,
+                               uint8_t* image_dev, uint64_t* keys_dev, void* stream) {
+  if (n < 0 || ntri < 0 || H < 1 || W < 1) return fail(1, "bad argument");
+  if (n == 0 || ntri == 0) return 0;
+  if (!verts_dev || !tris_dev || !colors_dev || !image_dev || !keys_dev) return fail(1, "null argument");
+  const int rc = pncc_render_launch(verts_dev, n, VGH_NUM_VERTS, tris_dev, ntri, colors_dev, H, W, image_dev,
+                                    reinterpret_cast<unsigned long long*>(keys_dev), static_cast<cudaStream_t>(stream));
+  if (rc == 2) return fail(1, "pncc: at most 4094 heads and 2^20-1 triangles per call");
+  return rc ? fail(5, "pncc launch failed: %s", cudaGetErrorString(cudaGetLastError())) : 0;
+}
+extern "C" int vgh_head_bbox(const float* verts_dev, int n, const int32_t* idx_dev, int n_idx, int32_t* out_xywh_dev, void* stream) {
+  if (n < 0 || n_idx < 1) return fail(1, "bad argument");
+  if (n == 0) return 0;
+  if (!verts_dev || !idx_dev || !out_xywh_dev) return fail(1, "null argument");
+  return head_bbox_launch(verts_dev, n, VGH_NUM_VERTS, idx_dev, n_idx, out_xywh_dev, static_cast<cudaStream_t>(stream))
+             ? fail(5, "head bbox launch failed: %s", cudaGetErrorString(cudaGetLastError())) : 0;
+}
+
 // ------------------------------------------------------------------------------------------ detector
 struct OpRt {
   vgh_op_desc d;
@@ -118,6 +138,7 @@ struct vgh_detector {
   // sparse heads: ops [n_dense_ops, n) run after select/NMS on survivor patches (one stack per head level)
   int n_dense_ops = 0, patch_cap = 0;
   bool sparse = false;
+  bool split = false;  // parity mode: activations as split bf16 terms, normal (pixels-on-M) conv kernel only
   int *head_level = nullptr, *head_patch = nullptr, *patch_src = nullptr, *level_rows = nullptr;
   cudaGraphExec_t graph = nullptr;
   cudaStream_t cap_stream = nullptr;  // capture needs a non-legacy stream; the graph then replays anywhere
@@ -280,7 +301,7 @@ static int build_conv(vgh_detector* d, OpRt& o) {
   L.Wo = q.up ? ib.W : (ib.W + q.stride - 1) / q.stride;
   // un-tuned default: the swapped kernel for Cout <= 128 on large maps and - with the tap reuse, which measured
   // faster than every other variant on every 3x3 stride-1 layer of the network - for all of those
-  L.swap = patch_op ? 1 : o.cfg_swap >= 0 ? o.cfg_swap
+  L.swap = d->split ? 0 : patch_op ? 1 : o.cfg_swap >= 0 ? o.cfg_swap
                            : (swap_eligible(q, ob) && (swap_forced() || (xr_eligible(q, ob) && xr_default()) ||
                                                        (q.cout <= 128 && !ob.fp32 && L.Ho * L.Wo >= 1024)) ? 1 : 0);
   if (L.swap) swap_groups(q, ob, L.ngroups, L.gw);
@@ -326,6 +347,8 @@ static int build_conv(vgh_detector* d, OpRt& o) {
   L.up_cout = q.up_cout;
   L.relu = q.relu;
   L.out_fp32 = ob.fp32;
+  L.split = (d->split && !ob.fp32) ? 1 : 0;
+  if (L.split && (q.cout % 32 || q.out_coff % 192 || (q.up && q.up_cout % 32))) return fail(2, "parity mode: channel slices must be whole 32-channel granules");
   if (q.up) {
     if (ob.H != 2 * ib.H || ob.W != 2 * ib.W) return fail(2, "transpose conv output buffer must be 2x the input");
   } else if (ob.H != L.Ho || ob.W != L.Wo) {
@@ -433,6 +456,8 @@ extern "C" int vgh_detector_create(const vgh_net_desc* n, const vgh_flame* flame
   d->bufs.assign(n->bufs, n->bufs + n->n_bufs);
   d->n_dense_ops = (n->n_dense_ops > 0 && n->n_dense_ops < n->n_ops) ? n->n_dense_ops : n->n_ops;
   d->sparse = d->n_dense_ops < n->n_ops;
+  d->split = n->split != 0;
+  if (d->split && d->sparse) return bail(fail(2, "parity (split) mode needs the dense-heads plan"));
   d->patch_cap = d->B * d->keep_k;
   if (d->sparse && (dmalloc(&d->head_level, (size_t)d->patch_cap) != cudaSuccess || dmalloc(&d->head_patch, (size_t)d->patch_cap) != cudaSuccess ||
                     dmalloc(&d->patch_src, (size_t)3 * d->patch_cap) != cudaSuccess || dmalloc(&d->level_rows, 4) != cudaSuccess))
@@ -506,7 +531,7 @@ static int launch_op(vgh_detector* d, OpRt& o, const uint8_t* images, cudaStream
   int rc = 0;
   switch (o.d.kind) {
     case VGH_OP_STEM:
-      rc = stem_pack_launch(images, static_cast<__nv_bfloat16*>(d->buf_ptr[o.d.out_buf]), d->B, d->S, s);
+      rc = stem_pack_launch(images, static_cast<__nv_bfloat16*>(d->buf_ptr[o.d.out_buf]), d->B, d->S, d->split ? 1 : 0, s);
       if (rc) return fail(5, "stem launch failed: %s", cudaGetErrorString(cudaGetLastError()));
       break;
     case VGH_OP_CONV:
@@ -515,7 +540,8 @@ static int launch_op(vgh_detector* d, OpRt& o, const uint8_t* images, cudaStream
       break;
     case VGH_OP_SPP: {
       const vgh_buf_desc& b = d->bufs[o.d.in_buf];
-      rc = spp_pool_launch(static_cast<__nv_bfloat16*>(d->buf_ptr[o.d.in_buf]), d->B, b.H, b.W, o.d.cin, s);
+      rc = d->split ? spp_pool_split_launch(static_cast<__nv_bfloat16*>(d->buf_ptr[o.d.in_buf]), d->B, b.H, b.W, o.d.cin, s)
+                    : spp_pool_launch(static_cast<__nv_bfloat16*>(d->buf_ptr[o.d.in_buf]), d->B, b.H, b.W, o.d.cin, s);
       if (rc) return fail(5, "spp launch failed");
       break;
     }
@@ -666,6 +692,7 @@ extern "C" int vgh_detector_autotune(vgh_detector* d, int iters, void* stream) {
   if (!d) return fail(1, "null argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (d->graph) { cudaGraphExecDestroy(d->graph); d->graph = nullptr; }
+  if (d->split) return 0;  // parity mode runs one fixed kernel configuration
   cudaEvent_t e0, e1;
   CUDA_OK(cudaEventCreate(&e0));
   CUDA_OK(cudaEventCreate(&e1));

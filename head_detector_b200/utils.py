@@ -36,6 +36,68 @@ def nms(boxes_xyxy, scores, flame_params, confidence_threshold: float = 0.5, iou
             flame_params[0].detach().float().to(dev)[keep])
 
 
+IMAGE_SIZE = 640
+
+
+def extend_bbox(bbox, offset=0.1) -> np.ndarray:
+    """utils.py:38-68: grow [x, y, w, h] by `offset` (one value, (w, h) or (left, right, top, bottom)) of its size per side."""
+    x, y, w, h = bbox
+    if isinstance(offset, tuple):
+        left, right, top, bottom = offset if len(offset) == 4 else (offset[0], offset[0], offset[1], offset[1])
+    else:
+        left = right = top = bottom = offset
+    return np.array([x - w * left, y - h * top, w * (1.0 + right + left), h * (1.0 + top + bottom)]).astype("int32")
+
+
+def extend_to_rect(bbox) -> np.ndarray:
+    """utils.py:71-78: the longer side on both axes, centred on the shorter one."""
+    x, y, w, h = bbox
+    if w > h:
+        return np.array([x, y - (w - h) // 2, w, w])
+    return np.array([x - (h - w) // 2, y, h, h])
+
+
+def flame_params_skull_center(flame_params, image: np.ndarray) -> Tuple[int, int]:
+    """utils.py:81-92 (letterbox geometry of detector.py:41-50 at the fixed IMAGE_SIZE, as the reference has it)."""
+    h, w = image.shape[:2]
+    scale = IMAGE_SIZE / max(h, w)
+    new_h, new_w = (IMAGE_SIZE, int(w * IMAGE_SIZE / h)) if h > w else (int(h * IMAGE_SIZE / w), IMAGE_SIZE)
+    c = (flame_params.translation / scale)[0].numpy()
+    return int(c[0] - (IMAGE_SIZE - new_w)), int(c[1] - (IMAGE_SIZE - new_h))
+
+
+def get_rotation_mat(img: np.ndarray, img_center, angle):
+    """utils.py:95-108: rotation about `img_center` with the canvas grown to the rotated bounds."""
+    import cv2
+
+    height, width = img.shape[:2]
+    m = cv2.getRotationMatrix2D(img_center, angle, 1.0)
+    abs_cos, abs_sin = abs(m[0, 0]), abs(m[0, 1])
+    bound_w, bound_h = int(height * abs_sin + width * abs_cos), int(height * abs_cos + width * abs_sin)
+    m[0, 2] += bound_w / 2 - img_center[0]
+    m[1, 2] += bound_h / 2 - img_center[1]
+    return m, (bound_w, bound_h)
+
+
+def vertically_align(img: np.ndarray, vertices: np.ndarray, flame_params, roll: float):
+    """utils.py:111-119: rotate the frame so that the head stands upright; vertices follow."""
+    import cv2
+
+    m, bounds = get_rotation_mat(img, flame_params_skull_center(flame_params, img), roll)
+    upright = cv2.warpAffine(img, m, bounds, flags=cv2.INTER_LINEAR)
+    return upright, np.hstack([vertices[:, :2], np.ones((vertices.shape[0], 1))]) @ m.T
+
+
+def refined_head_bbox(vertices: np.ndarray):
+    """utils.py:26-35 (host form; the batched device form is mesh.refined_head_bboxes)."""
+    from .head_info import Bbox
+    from .mesh import tables
+
+    pts = np.asarray(vertices)[tables()["head_indices"]]
+    x, y, x1, y1 = (int(v) for v in (pts[:, 0].min(), pts[:, 1].min(), pts[:, 0].max(), pts[:, 1].max()))
+    return Bbox(x=x, y=y, w=x1 - x, h=y1 - y)
+
+
 def rot_mat_from_6dof(v: torch.Tensor) -> torch.Tensor:
     """utils.py:120-128 (host-side helper for API objects; the decode kernel has its own copy)."""
     assert v.shape[-1] == 6

@@ -82,6 +82,19 @@ int vgh_select_nms(const float* boxes_dev, const float* scores_dev, int B, int A
 int vgh_letterbox(const uint8_t* src_dev, const int64_t* offsets, const int32_t* heights, const int32_t* widths, int n,
                   int image_size, uint8_t* out_dev, float* xform_host, void* stream);
 
+/* ---------------------------------------------------------------------------------- mesh consumers */
+/* `PredictionResult.get_pncc()`: PNCCProcessor.__call__ (head_detector/pncc_processor.py:66-73) over the CPU z-buffer
+ * rasteriser Sim3DR `_rasterize` (head_detector/Sim3DR/lib/rasterize_kernel.cpp:219-293), for all heads of an image in two
+ * launches, bit-identical.  verts_dev [n,5023,3] image-space vertices as HeadMetadata.vertices_3d holds them (the kernel
+ * uses depth = -z: the reference flips z in place before rasterising); tris_dev int32 [ntri,3]; colors_dev float
+ * [5023,3] in [0,1]; image_dev uint8 [H,W,3] painted in place (zero it for the reference's output); keys_dev: H*W
+ * uint64 workspace. */
+int vgh_pncc_render(const float* verts_dev, int n, const int32_t* tris_dev, int ntri, const float* colors_dev, int H, int W,
+                    uint8_t* image_dev, uint64_t* keys_dev, void* stream);
+/* `refined_head_bbox` (head_detector/utils.py:26-35) for n heads: int-truncated min / max of x, y over the vertex subset
+ * idx_dev int32 [n_idx] -> out_xywh_dev int32 [n,4] = (x, y, x1 - x, y1 - y). */
+int vgh_head_bbox(const float* verts_dev, int n, const int32_t* idx_dev, int n_idx, int32_t* out_xywh_dev, void* stream);
+
 /* ---------------------------------------------------------------------------------- conv network */
 /* Execution plan of the deploy-form network, produced by head_detector_b200/arch.py from the
  * reference's arch yaml (yolo_heads_l_arch_params.yaml).  Activations are NHWC bf16 buffers;
@@ -127,6 +140,11 @@ typedef struct {
   int32_t keep_k;                /* capacity of survivors per image (keep_top_k, utils.py:166) */
   int32_t n_dense_ops;           /* ops [0, n_dense_ops) run before select/NMS, the rest after it on survivor patches;
                                     0 or n_ops = single-phase (dense) plan */
+  int32_t split;                 /* parity mode (fp32-class arithmetic for end-to-end checks against the reference's fp32 path):
+                                    every bf16 activation y is stored as three bf16 terms h + m + l == y in six planes
+                                    [h|m|h|m|h|l] per 32-channel granule (buffers carry 6x the channels) and weights are packed
+                                    [w_h|w_h|w_m|w_m|w_l|w_h] along K, so that the bf16 MMAs accumulate the six leading partial
+                                    products in fp32 (relative error ~2^-22 per product instead of 2^-9).  Dense plan only. */
 } vgh_net_desc;
 
 int vgh_detector_create(const vgh_net_desc* net, const vgh_flame* flame, vgh_detector** out);

@@ -24,6 +24,8 @@ Fixtures written (all small, committed):
                          (oracle/sg_net.py traced; hf_hub_download patched to the local file): boxes, scores, vertices,
                          plus the stage timing of BASELINE configs[0] -> profiles/r2_reference_cpu_config0.json
                          (`python oracle/make_golden.py --only-net` rewrites these three)
+  pncc_ref.npz           reference `PredictionResult.get_pncc()` / `get_aligned_heads()` / `draw(...)` on four heads
+                         (PNCCProcessor + the Sim3DR C++ rasteriser compiled in place: oracle/Makefile -> oracle/_ref/)
 """
 import json
 import os
@@ -225,7 +227,44 @@ def detector_case():
     print("config 0 timing", t)
 
 
+def pncc_case():
+    """The reference's `PredictionResult.get_pncc()` / `get_aligned_heads()` / `draw()` on reference-decoded heads (three
+    of them overlapping): PNCCProcessor + Sim3DR C++ (compiled in place, oracle/Makefile)."""
+    import subprocess
+
+    subprocess.run(["make", "-C", HERE, "_ref/libsim3dr_ref.so"], check=True, capture_output=True)
+    from head_detector.detection_result import PredictionResult
+    from head_detector.head_info import Bbox, FlameParams, HeadMetadata
+    from head_detector.utils import calculate_rpy, refined_head_bbox
+
+    g = np.load(os.path.join(OUT, "flame_ref_heads.npz"))
+    verts = [g["projected"][0].copy(), g["projected"][1].copy(), g["projected"][2].copy(), g["projected"][0].copy() + np.float32([18.5, -11.25, 40.0])]
+    verts = [v + np.float32([150.0, -60.0, 0.0]) for v in verts]            # inside a 640x480 frame, the last one overlapping the first
+    params = torch.from_numpy(g["params"][[0, 1, 2, 0]])
+    heads = []
+    for v, p in zip(verts, params):
+        fp = FlameParams.from_3dmm(p[None])
+        bb = refined_head_bbox(v)
+        heads.append(HeadMetadata(bbox=bb, score=0.9, flame_params=fp, vertices_3d=v.copy(), head_pose=calculate_rpy(fp)))
+    rng = np.random.default_rng(3)
+    frame = rng.integers(0, 256, (480, 640, 3), dtype=np.uint8)
+    res = PredictionResult(frame, heads)
+    drawn = {m: res.draw(m) for m in ("full", "bbox", "landmarks", "points", "pose")}
+    crops = res.get_aligned_heads()
+    pncc = res.get_pncc()                                                    # flips z of every head in place (reference quirk)
+    print("pncc_ref: painted px", int((pncc.sum(2) != 0).sum()), "crops", [c.shape for c in crops])
+    np.savez_compressed(os.path.join(OUT, "pncc_ref.npz"), vertices=np.stack(verts), params=params.numpy(), frame_seed=np.array(3), pncc=pncc,
+                        bbox=np.array([[h.bbox.x, h.bbox.y, h.bbox.w, h.bbox.h] for h in heads]),
+                        **{f"draw_{k}_{part}": arr for k, v in drawn.items()      # only the pixels a draw method touched
+                           for part, arr in zip(("yx", "rgb"), (lambda m: (np.argwhere(m).astype(np.int16), v[m]))((v != frame).any(2)))},
+                        **{f"crop{i}": c for i, c in enumerate(crops)},
+                        z_after=np.stack([h.vertices_3d[:, 2] for h in heads]))
+
+
 def main():
+    if "--only-pncc" in sys.argv:
+        pncc_case()
+        return
     if "--only-letterbox" in sys.argv:
         letterbox_cases()
         return
@@ -300,6 +339,7 @@ def main():
     letterbox_cases()
     heads_cases()
     detector_case()
+    pncc_case()
     print("golden fixtures written to", OUT)
 
 

@@ -105,13 +105,9 @@ def test_empty_batch_and_errors():
 
 
 def test_head_detector_device_and_host_letterbox_agree():
-    import warnings
-
     from head_detector_b200 import HeadDetector
 
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        det = HeadDetector(image_size=128, batch_size=3)
+    det = HeadDetector(image_size=128, batch_size=3, weights="synthetic")
     imgs = [_rand((90, 160), 1), _rand((200, 100), 2)]
     det._device_letterbox = True
     fd, xd, cd = det._prepare_batch(imgs)

@@ -265,12 +265,15 @@ def test_parse_predictions_matches_reference_golden(golden_dir):
     n = params.shape[0]
     pad, scale = (0, 80), 0.5
     xf = torch.tensor([[pad[0], pad[1], scale]] * n).cuda()
-    _, rot, verts = flame.decode(params, xform=xf, live=(128, 64))
-    out = {"offsets": torch.tensor([0, n], dtype=torch.int32), "keep_boxes": torch.from_numpy(g["boxes"])[None].cuda(),
-           "keep_scores": torch.from_numpy(g["scores"])[None].cuda(), "vertices": verts, "params": params, "rotations": rot}
     det = object.__new__(HeadDetector)
-    det._image_size = 640
-    heads = det._parse_predictions(out, 0, {"padding": pad, "scale": scale})
+    det._image_size, det._flame = 640, flame
+    # the reference signature (detector.py:61): kept boxes, scores, 413-float rows, cache - decodes the vertices itself
+    heads = det._parse_predictions(torch.from_numpy(g["boxes"]).cuda(), torch.from_numpy(g["scores"]).cuda(), params, {"padding": pad, "scale": scale})
+    # ... and with the vertices the engine already decoded riding along in the cache (what _postprocess does)
+    _, rot, verts = flame.decode(params, xform=xf, live=(128, 64))
+    again = det._parse_predictions(torch.from_numpy(g["boxes"]).cuda(), torch.from_numpy(g["scores"]).cuda(), params,
+                                   {"padding": pad, "scale": scale, "_decoded": (verts, rot)})
+    assert all(np.array_equal(a.vertices_3d, b.vertices_3d) and a.bbox == b.bbox for a, b in zip(heads, again))
     assert [[int(v) for v in h.bbox] for h in heads] == g["bbox_xywh"].tolist()
     assert np.abs(np.stack([h.vertices_3d for h in heads]) - g["vertices_3d"]).max() < 1e-4 / scale
     assert np.allclose([[h.head_pose.roll, h.head_pose.pitch, h.head_pose.yaw] for h in heads], g["rpy"], atol=1e-3)

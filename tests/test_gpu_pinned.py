@@ -1,0 +1,187 @@
+"""GPU path against golden vectors produced by the reference's OWN code (tests/golden/heads_ref.npz, topk_ref.npz,
+detector_ref.npz; generator oracle/make_golden.py) and the fp32-class parity mode of the conv network.
+
+fast mode  = bf16 operands / bf16 activations (throughput mode): tolerances are bf16-sized and stated per check.
+parity mode = activations and weights as three bf16 terms, six partial products per MAC accumulated in fp32 on the same
+              tcgen05 kernels: tolerances are fp32-sized."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import net_oracle, nms_oracle, sg_net
+from oracle.make_golden import DETECTOR_SEED, HEADS_SEED, detector_image, detector_net, heads_feats
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOWERS = ("shape", "expr", "rot", "jaw", "transl", "scale")
+
+
+def _nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.fixture(scope="module")
+def heads_weights():
+    from head_detector_b200 import weights
+
+    return weights.deploy_from_state_dict(sg_net.build(HEADS_SEED).state_dict())
+
+
+def _raw_from_engine(eng, l):
+    from head_detector_b200 import arch
+
+    reg = eng.read_buffer(f"head{l}.reg_raw").permute(0, 3, 1, 2)
+    fl = eng.read_buffer(f"head{l}.flame_raw").permute(0, 3, 1, 2)
+    return reg[:, :68], reg[:, 68:69], {tw: fl[:, arch.RAW_ROW_OFF[tw]:arch.RAW_ROW_OFF[tw] + oc] for tw, _, oc in arch.TOWERS}
+
+
+@pytest.mark.parametrize("parity", [False, True])
+def test_heads_against_reference_class_outputs(heads_weights, parity):
+    """a4: the three head levels on the reference fixture's feature maps; raw outputs vs `YoloHeadsDFLHead` (reference run)."""
+    from head_detector_b200.engine import Engine
+
+    z = np.load(os.path.join(GOLD, "heads_ref.npz"))
+    eng = Engine(heads_weights, 2, 128, sparse_heads=False, parity=parity)
+    for name, f in zip(("p3", "p4", "p5"), heads_feats()):
+        eng.write_buffer(name, _nhwc(f))
+    eng.forward_from("head1.stems")
+    torch.cuda.synchronize()
+    worst = 0.0
+    for l in (1, 2, 3):
+        reg, cls, towers = _raw_from_engine(eng, l)
+        pairs = [(reg, z[f"reg{l}"]), (cls, z[f"cls{l}"])] + [(towers[tw], z[f"{tw}{l}"]) for tw in TOWERS]
+        for got, want in pairs:
+            scale = np.abs(want).max() + 1e-6
+            err = np.abs(got.numpy() - want).max() / scale
+            worst = max(worst, err)
+    # fast: bf16 rounding of weights and of three stored activations per branch; parity: fp32-class
+    assert worst < (3e-5 if parity else 2e-2), worst
+    boxes, scores = eng.boxes.cpu().numpy(), eng.scores.cpu().numpy()
+    flame = eng.dense_flame().cpu().numpy()
+    box_err = np.abs(boxes - z["boxes"]).max()
+    assert box_err < (2e-3 if parity else 1.0), box_err                       # pixels
+    assert np.abs(scores - z["scores"][..., 0]).max() < (1e-5 if parity else 2e-3)
+    rel = np.abs(flame - z["flame"]) / (np.abs(z["flame"]) + 1.0)
+    assert rel.max() < (1e-4 if parity else 0.1), rel.max()
+
+
+def test_decode_kernels_on_the_reference_raw_outputs(heads_weights):
+    """a5: box decode / FLAME row assembly fed with the REFERENCE's raw head outputs must give the reference's decoded
+    boxes / scores / flame[B,A,413] (yolo_head_ndfl_heads.py:137-172 incl. the 400..408 channel rotation)."""
+    from head_detector_b200 import arch
+    from head_detector_b200.engine import Engine
+
+    z = np.load(os.path.join(GOLD, "heads_ref.npz"))
+    eng = Engine(heads_weights, 2, 128, sparse_heads=False)
+    for l in (1, 2, 3):
+        reg, cls = torch.from_numpy(z[f"reg{l}"]), torch.from_numpy(z[f"cls{l}"])
+        b, _, h, w = reg.shape
+        rr = torch.zeros(b, h, w, arch.REG_ROWS)
+        rr[..., :68], rr[..., 68:69] = _nhwc(reg), _nhwc(cls)
+        fr = torch.zeros(b, h, w, arch.FLAME_ROWS)
+        for tw, _, oc in arch.TOWERS:
+            fr[..., arch.RAW_ROW_OFF[tw]:arch.RAW_ROW_OFF[tw] + oc] = _nhwc(torch.from_numpy(z[f"{tw}{l}"]))
+        eng.write_buffer(f"head{l}.reg_raw", rr)
+        eng.write_buffer(f"head{l}.flame_raw", fr)
+    eng.forward_from(None)
+    torch.cuda.synchronize()
+    assert np.abs(eng.boxes.cpu().numpy() - z["boxes"]).max() < 2e-4          # pixels; boxes span ~[-50, 180]
+    assert np.abs(eng.scores.cpu().numpy() - z["scores"][..., 0]).max() < 1e-6
+    flame = eng.dense_flame().cpu().numpy()
+    rel = np.abs(flame - z["flame"]) / (np.abs(z["flame"]) + 1.0)
+    assert rel.max() < 2e-6, rel.max()
+
+
+def test_select_nms_equals_reference_topk_module_plus_nms():
+    """a6/a7: VGGHeadDecodingModule (top-k 1000, yolo_heads.py:44-86) + utils.nms, run by the reference -> same kept ids."""
+    from head_detector_b200.utils import select_nms_indices
+
+    z = np.load(os.path.join(GOLD, "topk_ref.npz"))
+    idx, cnt = select_nms_indices(torch.from_numpy(z["boxes"]), torch.from_numpy(z["scores"]), 0.5, 0.5, 1000, 100)
+    idx, cnt = idx.cpu().numpy(), cnt.cpu().numpy()
+    for b in range(2):
+        assert idx[b, :cnt[b]].tolist() == z[f"keep{b}"].tolist()
+
+
+def test_parity_mode_whole_network_vs_fp32_oracle():
+    """a2/a3: every stage of the conv network in parity mode vs the fp32 oracle network on the same image; the same
+    numbers for the fast mode are printed (and bounded) so that the precision cost of bf16 is on record."""
+    from head_detector_b200.engine import Engine
+
+    w = net_oracle.synthetic_weights(3)
+    g = torch.Generator().manual_seed(4)
+    img = torch.randint(0, 256, (2, 128, 128, 3), generator=g, dtype=torch.uint8)
+    taps = {}
+    with torch.no_grad():
+        ob, os_, of = net_oracle.DeployNet(w).forward(img.permute(0, 3, 1, 2).float() / 255.0, taps)
+    report = {}
+    for parity in (True, False):
+        eng = Engine(w, 2, 128, sparse_heads=False, parity=parity)
+        boxes, scores = eng.forward(img.cuda())
+        torch.cuda.synchronize()
+        errs = {}
+        for name in ("c2", "c3", "c4", "c5", "p3", "p4", "p5"):
+            want = _nhwc(taps[name])
+            errs[name] = float((eng.read_buffer(name) - want).abs().max() / (want.abs().max() + 1e-6))
+        errs["boxes_px"] = float((boxes.cpu() - ob).abs().max())
+        errs["scores"] = float((scores.cpu() - os_[..., 0]).abs().max())
+        fl = eng.dense_flame().cpu()
+        errs["flame_rel"] = float(((fl - of).abs() / (of.abs() + 1.0)).max())
+        report["parity" if parity else "fast"] = errs
+    print("\nper-stage max error vs the fp32 oracle:", report)
+    p, f = report["parity"], report["fast"]
+    assert max(p[k] for k in ("c2", "c3", "c4", "c5", "p3", "p4", "p5")) < 2e-5, p
+    assert p["boxes_px"] < 2e-3 and p["scores"] < 1e-6 and p["flame_rel"] < 2e-4, p
+    assert max(f[k] for k in ("c2", "c3", "c4", "c5", "p3", "p4", "p5")) < 5e-2 and f["boxes_px"] < 2.0, f
+
+
+def _match(ref_boxes, got_boxes):
+    """greedy IoU matching of xywh boxes -> list of (ref index, got index, iou)"""
+    def iou(a, b):
+        ax2, ay2, bx2, by2 = a[0] + a[2], a[1] + a[3], b[0] + b[2], b[1] + b[3]
+        iw, ih = max(0, min(ax2, bx2) - max(a[0], b[0])), max(0, min(ay2, by2) - max(a[1], b[1]))
+        inter = iw * ih
+        return inter / max(a[2] * a[3] + b[2] * b[3] - inter, 1e-9)
+    out, used = [], set()
+    for i, rb in enumerate(ref_boxes):
+        best = max(((iou(rb, gb), j) for j, gb in enumerate(got_boxes) if j not in used), default=(0, -1))
+        if best[1] >= 0 and best[0] > 0.5:
+            used.add(best[1])
+            out.append((i, best[1], best[0]))
+    return out
+
+
+@pytest.mark.parametrize("parity", [True, False])
+def test_head_detector_end_to_end_vs_unmodified_reference(tmp_path, parity):
+    """The whole public path - TorchScript blob -> HeadDetector(...)(image) - against detector_ref.npz, the output of the
+    UNMODIFIED reference HeadDetector (torch-CPU fp32) on the same synthetic blob and the same 480x640 frame."""
+    from head_detector_b200 import HeadDetector
+
+    z = np.load(os.path.join(GOLD, "detector_ref.npz"))
+    assert int(z["seed"]) == DETECTOR_SEED
+    blob = sg_net.trace_to(str(tmp_path / "vgg_heads_l.trcd"), detector_net(), 64)   # parameters do not depend on the traced size
+    det = HeadDetector(weights=blob, parity=parity, device_letterbox=False)
+    res = det(detector_image(), confidence_threshold=0.5)
+    got_boxes = np.array([[int(v) for v in h.bbox] for h in res.heads]).reshape(-1, 4)
+    n_ref = len(z["scores"])
+    pairs = _match(z["bbox_xywh"], got_boxes)
+    print(f"\nparity={parity}: reference heads {n_ref}, ours {len(res.heads)}, matched {len(pairs)}")
+    if parity:
+        # fp32-class arithmetic: the same heads in the same order (a borderline candidate may flip at the 0.5 threshold)
+        assert abs(len(res.heads) - n_ref) <= 2 and len(pairs) >= n_ref - 2
+        same_order = [(i, j) for i, j, _ in pairs if i == j]
+        assert len(same_order) >= n_ref - 4
+        for i, j in same_order[:40]:
+            assert np.abs(got_boxes[j] - z["bbox_xywh"][i]).max() <= 1
+            assert abs(float(res.heads[j].score) - z["scores"][i]) < 1e-4
+        for i, j in [p for p in same_order if p[0] < len(z["vertices_3d"])]:
+            err = np.abs(res.heads[j].vertices_3d - z["vertices_3d"][i]).max()
+            assert err < 0.05, (i, err)     # pixels at scale ~1e3: fp32 rounding of the two networks' different op order
+            rpy = res.heads[j].head_pose
+            assert np.abs(np.array([rpy.roll, rpy.pitch, rpy.yaw]) - z["rpy"][i]).max() < 0.05
+    else:
+        # bf16 throughput mode on random weights: most heads survive, boxes move by a few pixels
+        assert len(pairs) >= 0.7 * n_ref
+        assert np.median([np.abs(got_boxes[j] - z["bbox_xywh"][i]).max() for i, j, _ in pairs]) <= 6
