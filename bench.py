@@ -220,6 +220,69 @@ def parity_check(eng, boxes, scores, batch):
         return {"error": repr(ex)}
 
 
+def parity_end_to_end(weights, batch=2):
+    """End-to-end precision of the conv path on `batch` images of the workload, with oracle/ as the checker: the fp32
+    oracle network (torch-CPU) against (a) the throughput mode (bf16 operands, bf16 activations) and (b) the parity mode
+    (three-term split bf16: fp32-class arithmetic on the same tensor-core kernels).  Per stage max-abs-error relative to
+    the stage's max |value|; then, on REAL network outputs (threshold at the 99.5th score percentile, as random weights
+    never reach 0.5): are the kept anchor ids those of `utils.nms` on the oracle's boxes / scores, and how far are the
+    decoded vertices from the oracle's (bar of the metric: 1e-4 px)."""
+    try:
+        import numpy as np
+        import torch
+
+        from head_detector_b200 import synth
+        from head_detector_b200.engine import Engine
+        from oracle import flame_oracle, net_oracle, nms_oracle
+
+        img = synth.synthetic_images(batch, IMAGE_SIZE, seed=4242)
+        taps = {}
+        with torch.no_grad():
+            ob, os_, of = net_oracle.DeployNet(weights).forward(img.permute(0, 3, 1, 2).float() / 255.0, taps)
+        thr = float(torch.quantile(os_.flatten(), 0.995))
+        consts = flame_oracle.load_flame_constants()
+        want_ids = [nms_oracle.select_nms(ob[b].numpy(), os_[b, :, 0].numpy(), thr, IOU, TOPK, 100) for b in range(batch)]
+        out = {"batch": batch, "conf_threshold": thr, "reference_heads": [int(len(k)) for k in want_ids],
+               "checker": "oracle/net_oracle.DeployNet (torch-CPU fp32) + utils.nms / FLAME restatements on the same images"}
+        for mode in ("parity", "fast"):
+            eng = Engine(weights, batch, IMAGE_SIZE, sparse_heads=False, parity=(mode == "parity"))
+            boxes, scores = eng.forward(img.cuda())
+            eng.postprocess(thr, IOU, TOPK)
+            torch.cuda.synchronize()
+            stage = {}
+            for name in ("c2", "c3", "c4", "c5", "p3", "p4", "p5"):
+                want = taps[name].permute(0, 2, 3, 1)
+                stage[name] = float((eng.read_buffer(name) - want).abs().max() / (want.abs().max() + 1e-6))
+            r = {"stage_rel_err": stage, "boxes_max_abs_err_px": float((boxes.cpu() - ob).abs().max()),
+                 "scores_max_abs_err": float((scores.cpu() - os_[..., 0]).abs().max())}
+            off, cnt, idx = eng.head_offsets.cpu().numpy(), eng.keep_cnt.cpu().numpy(), eng.keep_idx.cpu().numpy()
+            r["nms_ids_equal_reference"] = bool(all(idx[b, :cnt[b]].tolist() == want_ids[b].tolist() for b in range(batch)))
+            r["heads"] = [int(c) for c in cnt]
+            verr, matched = 0.0, 0
+            n = int(off[-1])
+            if n:
+                verts = eng.head_verts(n).cpu()
+                for b in range(batch):
+                    ids = idx[b, :cnt[b]].tolist()
+                    ref_rows = {a: i for i, a in enumerate(want_ids[b].tolist())}
+                    common = [a for a in ids if a in ref_rows]
+                    if not common:
+                        continue
+                    ref_v = flame_oracle.detector_vertices(of[b][torch.tensor(common)], consts)
+                    got_v = verts[off[b]:off[b + 1]][[ids.index(a) for a in common]]
+                    verr = max(verr, float((got_v - ref_v).abs().max()))
+                    matched += len(common)
+            r["vertices_3d_max_abs_err_px"], r["heads_compared"] = verr, matched
+            out[mode] = r
+            del eng
+            torch.cuda.empty_cache()
+        return out
+    except Exception as ex:  # never lose the measurement line to the checker
+        import traceback
+
+        return {"error": repr(ex), "trace": traceback.format_exc()[-600:]}
+
+
 # ------------------------------------------------------------------------------------------ GPU arm
 class Pipeline:
     """Two engines per GPU = two batches in flight: the select/NMS/FLAME tail of batch i (few, small kernels) overlaps
@@ -485,6 +548,8 @@ def run_ours(args, rank, world, local_rank):
             line["dense_heads"] = extra_dense(args, weights, B)
         except Exception as ex:  # never lose the headline to an extra
             line["dense_heads"] = {"error": repr(ex)}
+        torch.cuda.empty_cache()
+        line["parity"]["end_to_end"] = parity_end_to_end(weights)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

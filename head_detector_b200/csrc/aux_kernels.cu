@@ -8,6 +8,7 @@
 #include <cstdio>
 
 #include "aux_kernels.cuh"
+#include "device_attr.cuh"
 
 namespace vgh {
 
@@ -128,11 +129,8 @@ int spp_pool_launch(__nv_bfloat16* buf, int B, int H, int W, int C, cudaStream_t
   while (CH > 8 && static_cast<size_t>(H) * W * CH * 2 * 3 > 160 * 1024) CH >>= 1;
   if (C % CH) return 1;
   const size_t smem = static_cast<size_t>(H) * W * CH * 2 * 3;
-  static size_t configured = 0;
-  if (smem > configured) {
-    if (cudaFuncSetAttribute(spp_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
-    configured = smem;
-  }
+  static SmemOptIn opt_in;
+  if (ensure_dynamic_smem(spp_pool_kernel, opt_in, smem) != cudaSuccess) return 1;
   spp_pool_kernel<<<B * (C / CH), 256, smem, stream>>>(buf, B, H, W, C, CH);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
@@ -410,7 +408,7 @@ __global__ void __launch_bounds__(1024) patch_assign_kernel(const DecodeLevels l
           if (p < cap) {
             head_level[offsets[b] + j] = q;
             head_patch[offsets[b] + j] = p;
-            patch_src[q * cap + p] = (b << 20) | (y << 10) | x;
+            patch_src[q * cap + p] = static_cast<int>((static_cast<unsigned>(b) << 20) | (static_cast<unsigned>(y) << 10) | static_cast<unsigned>(x));
           }
         }
         run[q] += __popc(m);
@@ -435,7 +433,7 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(const __nv_bfloat16* 
   const int vec = C >> 3;  // uint4 = 8 bf16
   for (int p = blockIdx.x; p < n_patches; p += gridDim.x) {  // grid = a few CTAs per SM, not the patch capacity
     const int src = patch_src[p];
-    const int b = src >> 20, y0 = ((src >> 10) & 1023) - kPatchC, x0 = (src & 1023) - kPatchC;
+    const int b = static_cast<int>(static_cast<unsigned>(src) >> 20), y0 = ((src >> 10) & 1023) - kPatchC, x0 = (src & 1023) - kPatchC;
     for (int i = threadIdx.x; i < kPatch * kPatch * vec; i += blockDim.x) {
       const int pix = i / vec, v = i - pix * vec;
       const int r = pix / kPatch, c = pix - r * kPatch;

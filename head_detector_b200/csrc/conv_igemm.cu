@@ -1,4 +1,5 @@
 #include "conv_igemm.cuh"
+#include "device_attr.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -378,16 +379,7 @@ bool conv_pdl_enabled() {
   return on == 1;
 }
 
-static int g_num_sms = 0;
-static int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0, n = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    g_num_sms = n;
-  }
-  return g_num_sms;
-}
+static int num_sms() { return device_sm_count(); }
 
 int conv_default_mt(int block_n) {
   // M tiles per CTA sharing one weight stream, such that two accumulator stages still fit in the
@@ -514,15 +506,14 @@ int conv_make_io_maps(ConvLaunch& L, void* out_base, const void* res_base) {
 
 template <int BK>
 static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
-  static size_t configured = 0;
+  static SmemOptIn opt_in;
   const size_t smem = conv_smem_bytes(L, BK);
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {
+    cudaError_t e = ensure_dynamic_smem(conv_igemm_kernel<BK>, opt_in, smem);
     if (e != cudaSuccess) {
       snprintf(g_conv_err, sizeof(g_conv_err), "set smem %zu failed: %s", smem, cudaGetErrorString(e));
       return 4;
     }
-    configured = smem;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(L.num_items < num_sms() ? L.num_items : num_sms());

@@ -42,6 +42,7 @@
 #include <cstdio>
 
 #include "conv_igemm.cuh"
+#include "device_attr.cuh"
 #include "ptx.cuh"
 
 namespace vgh {
@@ -404,15 +405,14 @@ size_t conv_swap_smem_bytes(const ConvLaunch& L, int bk) {
 
 template <int BK, bool XR>
 static int launch_swap_t(const ConvLaunch& L, int sms, cudaStream_t stream, char* err, size_t errlen) {
-  static size_t configured = 0;
+  static SmemOptIn opt_in;
   const size_t smem = conv_swap_smem_bytes(L, BK);
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_swap_kernel<BK, XR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {
+    cudaError_t e = ensure_dynamic_smem(conv_igemm_swap_kernel<BK, XR>, opt_in, smem);
     if (e != cudaSuccess) {
       snprintf(err, errlen, "swap conv: set smem %zu failed: %s", smem, cudaGetErrorString(e));
       return 4;
     }
-    configured = smem;
   }
   cudaLaunchConfig_t cfg{};
   const int n_cl = L.cluster > 1 ? L.cluster : 1;

@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "flame_decode.cuh"
+#include "device_attr.cuh"
 
 namespace vgh {
 
@@ -390,14 +391,13 @@ static int launch_flame(const FlameArgs& a, cudaStream_t stream, char* err, size
   const int lt = a.ns + a.ne + kNPose;
   const int lt_pad = (lt + kLc - 1) / kLc * kLc;
   const size_t smem = flame_smem_bytes(heads, lt_pad);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(flame_decode_kernel<HG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static SmemOptIn opt_in;
+  {
+    cudaError_t e = ensure_dynamic_smem(flame_decode_kernel<HG>, opt_in, smem);
     if (e != cudaSuccess) {
       snprintf(err, errlen, "flame smem %zu: %s", smem, cudaGetErrorString(e));
       return 2;
     }
-    configured = smem;
   }
   int dev = 0, sms = 148, per_sm = 1;
   cudaGetDevice(&dev);

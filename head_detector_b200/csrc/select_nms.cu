@@ -18,6 +18,7 @@
 #include <cstdio>
 
 #include "select_nms.cuh"
+#include "device_attr.cuh"
 
 namespace vgh {
 
@@ -197,14 +198,13 @@ int select_nms_launch(const float* boxes, const float* scores, int B, int A, flo
   }
   NmsArgs p{boxes, scores, A, conf_thr, iou_thr, top_k, keep_k, keep_idx, keep_cnt, keep_boxes, keep_scores};
   const size_t smem = kMaxCand * (8 + 16 + 4 + 32 * 4);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(select_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static SmemOptIn opt_in;
+  {
+    cudaError_t e = ensure_dynamic_smem(select_nms_kernel, opt_in, smem);
     if (e != cudaSuccess) {
       snprintf(err, errlen, "select_nms smem: %s", cudaGetErrorString(e));
       return 2;
     }
-    configured = true;
   }
   select_nms_kernel<<<B, kNmsThreads, smem, stream>>>(p);
   cudaError_t e = cudaGetLastError();

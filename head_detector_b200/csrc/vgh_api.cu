@@ -458,6 +458,8 @@ extern "C" int vgh_detector_create(const vgh_net_desc* n, const vgh_flame* flame
   d->sparse = d->n_dense_ops < n->n_ops;
   d->split = n->split != 0;
   if (d->split && d->sparse) return bail(fail(2, "parity (split) mode needs the dense-heads plan"));
+  // survivor patches are addressed as image << 20 | y << 10 | x (aux_kernels.cu: patch_src)
+  if (d->sparse && (d->B > 4096 || d->S / 8 > 1024)) return bail(fail(1, "sparse heads: batch <= 4096 and image size <= 8192"));
   d->patch_cap = d->B * d->keep_k;
   if (d->sparse && (dmalloc(&d->head_level, (size_t)d->patch_cap) != cudaSuccess || dmalloc(&d->head_patch, (size_t)d->patch_cap) != cudaSuccess ||
                     dmalloc(&d->patch_src, (size_t)3 * d->patch_cap) != cudaSuccess || dmalloc(&d->level_rows, 4) != cudaSuccess))

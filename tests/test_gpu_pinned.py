@@ -56,8 +56,9 @@ def test_heads_against_reference_class_outputs(heads_weights, parity):
             scale = np.abs(want).max() + 1e-6
             err = np.abs(got.numpy() - want).max() / scale
             worst = max(worst, err)
-    # fast: bf16 rounding of weights and of three stored activations per branch; parity: fp32-class
-    assert worst < (3e-5 if parity else 2e-2), worst
+    # fast: bf16 rounding of weights and of three stored activations per branch; parity: fp32-class - what is left is the
+    # fp32 rounding of the re-parameterised weights against the reference's unfused blocks (3e-5 on the CPU, tests/test_oracle_sg.py)
+    assert worst < (1e-4 if parity else 2e-2), worst
     boxes, scores = eng.boxes.cpu().numpy(), eng.scores.cpu().numpy()
     flame = eng.dense_flame().cpu().numpy()
     box_err = np.abs(boxes - z["boxes"]).max()
