@@ -13,7 +13,7 @@ NUM_PARAMS = 413
 
 (OUT_BOXES, OUT_SCORES, OUT_KEEP_IDX, OUT_KEEP_CNT, OUT_KEEP_BOXES, OUT_KEEP_SCORES, OUT_HEAD_OFFSETS, OUT_HEAD_PARAMS,
  OUT_HEAD_VERTS, OUT_HEAD_ROT, OUT_INPUT) = range(11)
-OP_STEM, OP_CONV, OP_SPP, OP_PATCH_GATHER, OP_PATCH_MASK = 0, 1, 2, 3, 4
+OP_STEM, OP_CONV, OP_SPP, OP_PATCH_GATHER, OP_PATCH_MASK, OP_STEM_CONV = 0, 1, 2, 3, 4, 5
 
 
 class BufDesc(C.Structure):

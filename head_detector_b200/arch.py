@@ -139,17 +139,22 @@ class Plan:
             self.simple(name + ".conv3", (cat, 0, 2 * hid), dst, cout)
 
 
-def build_plan(image_size: int = 640, sparse_heads: Optional[Tuple[int, int]] = None) -> Plan:
+def build_plan(image_size: int = 640, sparse_heads: Optional[Tuple[int, int]] = None, fused_stem: bool = True) -> Plan:
     """`sparse_heads=(batch, keep_top_k)` builds the two-phase plan: the dense ops end with the box branch; the FLAME
-    branch of every level follows select/NMS and runs on survivor patches (see PATCH)."""
+    branch of every level follows select/NMS and runs on survivor patches (see PATCH).  `fused_stem=False` keeps the
+    two-op stem (uint8 im2col buffer + Cin = 32 1x1 conv on the tensor-core GEMM kernel) that the parity mode splits."""
     P = Plan(image_size)
     if sparse_heads is not None:
         P.patch_cap = int(sparse_heads[0]) * int(sparse_heads[1])
     S = image_size
-    cols = P.buf("stem.cols", S // 2, 32)   # im2col rows of the uint8 image: 27 taps (ky,kx,c) + 5 zeros
-    P.ops.append(Op(_lib.OP_STEM, (0, 0, 3), (cols, 0), 32, 3, 2, 0, label="stem.im2col"))
-    stem = P.buf("stem", S // 2, 64)        # 48 real channels + 16 zeros (64-wide K blocks downstream)
-    P.conv("stem", (cols, 0, 32), (stem, 0), [Part("stem", 0, STEM_OUT, [(0, 0, 27)])], cout=64)
+    if fused_stem:   # one kernel: uint8 window -> im2col fragments in registers -> MMA -> bias + ReLU -> 64-channel rows
+        stem = P.buf("stem", S // 2, 64)    # 48 real channels + 16 zeros (64-wide K blocks downstream)
+        P.ops.append(Op(_lib.OP_STEM_CONV, (0, 0, 32), (stem, 0), 64, 1, 1, 1, parts=[Part("stem", 0, STEM_OUT, [(0, 0, 27)])], label="stem"))
+    else:
+        cols = P.buf("stem.cols", S // 2, 32)   # im2col rows of the uint8 image: 27 taps (ky,kx,c) + 5 zeros
+        P.ops.append(Op(_lib.OP_STEM, (0, 0, 3), (cols, 0), 32, 3, 2, 0, label="stem.im2col"))
+        stem = P.buf("stem", S // 2, 64)
+        P.conv("stem", (cols, 0, 32), (stem, 0), [Part("stem", 0, STEM_OUT, [(0, 0, 27)])], cout=64)
     prev, prev_c, res = stem, 64, S // 2
     feats = []
     for i, (cout, n, hid) in enumerate(BACKBONE, start=1):
@@ -289,6 +294,7 @@ def split_plan(P: Plan) -> Plan:
     is_bf16 = [not fp32 for (_, _, _, fp32) in P.bufs]
     P.bufs = [(h, w, c * SPLIT_PLANES if not fp32 else c, fp32) for (h, w, c, fp32) in P.bufs]
     for op in P.ops:
+        assert op.kind != _lib.OP_STEM_CONV, "parity mode splits the two-op stem: build_plan(fused_stem=False)"
         if op.kind == _lib.OP_STEM:
             continue
         if op.kind == _lib.OP_SPP:   # the kernel works in logical channels
@@ -333,7 +339,7 @@ def pack(plan: Plan, w: Dict[str, torch.Tensor]) -> PackedNet:
     wchunks, bchunks, meta = [], [], []
     w_off = b_off = 0
     for op in plan.ops:
-        if op.kind != _lib.OP_CONV:
+        if op.kind not in (_lib.OP_CONV, _lib.OP_STEM_CONV):
             meta.append({})
             continue
         cin, taps = op.src[2] // (SPLIT_PLANES if plan.split else 1), op.k * op.k   # logical channels per tap
@@ -482,12 +488,12 @@ def total_macs(image_size: int = 640) -> int:
     tot = 3 * STEM_OUT * 9 * (image_size // 2) ** 2
     for op in P.ops:
         if op.kind != _lib.OP_CONV:
-            continue
+            continue   # (the stem, fused or not, is counted above with its true K = 27)
         src_res = P.bufs[op.src[0]][0]
         out_res = src_res if op.up else src_res // op.stride
         for p in op.parts:
             if p.name == "stem":
-                continue  # counted above with its true K = 27
+                continue
             cin = sum(s[2] for s in p.segs)
             tot += cin * p.cout * out_res * out_res * (1 if p.transposed else op.k * op.k)
     return tot

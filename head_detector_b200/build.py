@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvggheads_b200.so")
-SOURCES = ["vgh_api.cu", "conv_igemm.cu", "conv_igemm_swap.cu", "flame_decode.cu", "select_nms.cu", "aux_kernels.cu", "letterbox.cu", "gather.cu", "mesh_kernels.cu"]
+SOURCES = ["vgh_api.cu", "conv_igemm.cu", "conv_igemm_swap.cu", "flame_decode.cu", "select_nms.cu", "aux_kernels.cu", "letterbox.cu", "gather.cu", "mesh_kernels.cu", "stem_conv.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 

@@ -5,8 +5,8 @@
 // work; IoU arithmetic uses non-contracted fp32 intrinsics in torchvision's operation order so the
 // kept anchor ids are bit-identical to the CPU reference on identical inputs.
 //
-//   1. candidates = {a : score[a] >= conf_thr}; key = score_bits<<32 | ~a  (descending key order ==
-//      descending score, ties -> lower anchor id first)
+//   1. candidates = {a : score[a] >= conf_thr}; key = ordered(score_bits)<<32 | ~a  (descending key order ==
+//      descending score for any sign, ties -> lower anchor id first)
 //   2. if more than top_k candidates: 8-bit MSB radix select of the top_k-th key
 //   3. compaction into shared memory, bitonic sort (descending)
 //   4. n x n suppression bit matrix in shared memory (n <= 1024)
@@ -37,8 +37,11 @@ struct NmsArgs {
   float* keep_scores; // optional [B,keep_k]
 };
 
+// order-preserving float -> uint map (negative scores sort below positive ones; -0.0 < +0.0 only in the tie-break)
 __device__ __forceinline__ unsigned long long make_key(float s, int a) {
-  return (static_cast<unsigned long long>(__float_as_uint(s)) << 32) | static_cast<unsigned>(~static_cast<unsigned>(a));
+  const unsigned u = __float_as_uint(s);
+  const unsigned ord = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return (static_cast<unsigned long long>(ord) << 32) | static_cast<unsigned>(~static_cast<unsigned>(a));
 }
 
 __global__ void __launch_bounds__(kNmsThreads) select_nms_kernel(const NmsArgs p) {
@@ -179,7 +182,7 @@ __global__ void __launch_bounds__(kNmsThreads) select_nms_kernel(const NmsArgs p
         const int a = static_cast<int>(~static_cast<unsigned>(k & 0xffffffffull));
         out_idx[kept] = a;
         if (p.keep_boxes) reinterpret_cast<float4*>(p.keep_boxes)[static_cast<size_t>(b) * p.keep_k + kept] = sbox[i];
-        if (p.keep_scores) p.keep_scores[static_cast<size_t>(b) * p.keep_k + kept] = __uint_as_float(static_cast<unsigned>(k >> 32));
+        if (p.keep_scores) p.keep_scores[static_cast<size_t>(b) * p.keep_k + kept] = sc[a];
       }
       ++kept;
     }

@@ -536,6 +536,15 @@ static int launch_op(vgh_detector* d, OpRt& o, const uint8_t* images, cudaStream
       rc = stem_pack_launch(images, static_cast<__nv_bfloat16*>(d->buf_ptr[o.d.out_buf]), d->B, d->S, d->split ? 1 : 0, s);
       if (rc) return fail(5, "stem launch failed: %s", cudaGetErrorString(cudaGetLastError()));
       break;
+    case VGH_OP_STEM_CONV: {
+      const vgh_buf_desc& ob = d->bufs[o.d.out_buf];
+      if (ob.fp32 || ob.H != d->S / 2 || o.d.k_total != 32 || o.d.cout != 64 || o.d.out_coff != 0)
+        return fail(2, "fused stem: expects a bf16 [S/2,S/2,>=64] output at channel 0 and 32-wide packed taps");
+      rc = stem_conv_launch(images, d->weights + o.d.w_off, d->bias + o.d.b_off, static_cast<__nv_bfloat16*>(d->buf_ptr[o.d.out_buf]), d->B, d->S,
+                            ob.C, o.d.relu, s);
+      if (rc) return fail(5, "fused stem launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+      break;
+    }
     case VGH_OP_CONV:
       rc = conv_launch(o.L, o.bk, s);
       if (rc) return fail(5, "%s", conv_last_error());
@@ -622,7 +631,7 @@ static int run_ops(vgh_detector* d, int op_begin, int op_end, const uint8_t* ima
       lane_joined[lane] = 1;
     }
     if (L > 1) {
-      int reads[2] = {o.d.kind == VGH_OP_STEM ? -1 : o.d.in_buf, o.d.kind == VGH_OP_CONV ? o.d.res_buf : -1};
+      int reads[2] = {(o.d.kind == VGH_OP_STEM || o.d.kind == VGH_OP_STEM_CONV) ? -1 : o.d.in_buf, o.d.kind == VGH_OP_CONV ? o.d.res_buf : -1};
       for (int b : reads) {
         if (b < 0) continue;
         for (int l2 = 0; l2 < L; ++l2) { int rc = depend(lane, last_w[b * L + l2]); if (rc) return rc; }

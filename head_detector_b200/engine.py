@@ -35,7 +35,7 @@ class Engine:
             sparse_heads = os.environ.get("VGGHEADS_B200_SPARSE_HEADS", "0") == "1"
         self.parity = bool(parity)
         self.sparse_heads = bool(sparse_heads) and not self.parity
-        self.plan = arch.build_plan(self.S, sparse_heads=(self.B, self.keep_k) if self.sparse_heads else None)
+        self.plan = arch.build_plan(self.S, sparse_heads=(self.B, self.keep_k) if self.sparse_heads else None, fused_stem=not self.parity)
         if self.parity:
             self.plan = arch.split_plan(self.plan)
         self.packed = arch.pack(self.plan, weights)

@@ -59,9 +59,9 @@ int vgh_flame_decode(const vgh_flame* f, const float* params_dev, int n, int n_s
                      const float* xform_dev, float* verts_dev, float* rot_dev, float* proj_dev, void* stream);
 
 /* ---------------------------------------------------------------------------------- select + NMS */
-/* boxes_dev [B,A,4] xyxy, scores_dev [B,A] (>= 0).  Per image: score >= conf_thr, best top_k
- * (<= 1024) by score, greedy NMS (suppress iff IoU > iou_thr), first keep_k survivors in
- * descending-score order.  keep_idx_dev [B,keep_k] int32 ORIGINAL anchor ids (-1 padded),
+/* boxes_dev [B,A,4] xyxy, scores_dev [B,A] (any sign).  Per image: score >= conf_thr, best top_k
+ * by score (top_k <= 1024: the candidate set lives in shared memory; the reference's only call site uses 1000,
+ * utils.py:163-166), greedy NMS (suppress iff IoU > iou_thr), first keep_k survivors in descending-score order.  keep_idx_dev [B,keep_k] int32 ORIGINAL anchor ids (-1 padded),
  * keep_cnt_dev [B] int32; keep_boxes_dev [B,keep_k,4] / keep_scores_dev [B,keep_k] optional. */
 int vgh_select_nms(const float* boxes_dev, const float* scores_dev, int B, int A, float conf_thr, float iou_thr,
                    int top_k, int keep_k, int32_t* keep_idx_dev, int32_t* keep_cnt_dev, float* keep_boxes_dev,
@@ -110,8 +110,10 @@ typedef struct {
  * Sparse heads (n_dense_ops < n_ops): the FLAME branch of a head level is only read at the anchors that survive
  * NMS and its receptive field there is 7x7 pixels, so its ops run AFTER select/NMS on 8x8 windows gathered around
  * the survivors (VGH_OP_PATCH_GATHER), stacked as one tall image per level; VGH_OP_PATCH_MASK zeroes the window
- * pixels outside the feature map (the dense graph's conv padding).  Such ops carry level = 1 + head level. */
-enum { VGH_OP_STEM = 0, VGH_OP_CONV = 1, VGH_OP_SPP = 2, VGH_OP_PATCH_GATHER = 3, VGH_OP_PATCH_MASK = 4 };
+ * pixels outside the feature map (the dense graph's conv padding).  Such ops carry level = 1 + head level.
+ * VGH_OP_STEM_CONV: the whole stem in one kernel (uint8 image -> 3x3 stride-2 conv, K = 27 padded to 32, + bias + ReLU ->
+ * bf16 with 64 stored channels); carries the weight fields of a conv op (n_pad rows of k_total = 32). */
+enum { VGH_OP_STEM = 0, VGH_OP_CONV = 1, VGH_OP_SPP = 2, VGH_OP_PATCH_GATHER = 3, VGH_OP_PATCH_MASK = 4, VGH_OP_STEM_CONV = 5 };
 
 typedef struct {
   int32_t kind;

@@ -42,6 +42,15 @@ def apply_op(pk, op, m, bufs, images_u8=None, emulate_bf16=True, patches=None):
         cols = cols.view(Bn, 3, 9, L).permute(0, 3, 2, 1).reshape(Bn, Ho, Ho, 27)   # -> (ky,kx,c) order
         bufs[op.dst[0]][..., :27] = cols
         bufs[op.dst[0]][..., 27:] = 0
+    elif op.kind == _lib.OP_STEM_CONV:  # fused stem: the same im2col rows times the packed [n_pad][32] taps, + bias, ReLU
+        x = images_u8.permute(0, 3, 1, 2).float()
+        cols = F.unfold(x, kernel_size=3, padding=1, stride=2)
+        Bn, _, L = cols.shape
+        Ho = images_u8.shape[1] // 2
+        cols = cols.view(Bn, 3, 9, L).permute(0, 3, 2, 1).reshape(Bn, Ho, Ho, 27)
+        wts = torch.from_numpy(pk.weights[m["w_off"]:m["w_off"] + m["n_pad"] * 32].view(np.int16).copy()).view(torch.bfloat16).float().reshape(m["n_pad"], 32)
+        y = cols @ wts[:op.cout, :27].T + torch.from_numpy(pk.bias[m["b_off"]:m["b_off"] + op.cout])
+        bufs[op.dst[0]][..., :op.cout] = rnd(F.relu(y) if op.relu else y)
     elif op.kind == _lib.OP_SPP:
         b = bufs[op.src[0]]
         C = op.src[2]

@@ -65,6 +65,20 @@ def test_ties_break_by_lower_anchor_id():
     assert _gpu(boxes[None], scores[None])[0] == no.select_nms(boxes, scores).tolist() == list(range(64))
 
 
+def test_negative_scores_with_non_positive_threshold():
+    """Raw logits instead of probabilities: scores of both signs, threshold <= 0 (round 1 ordered keys by raw float bits,
+    which sorts negative floats upside down)."""
+    rng = np.random.default_rng(5)
+    boxes, _ = clustered_anchors(8400, 30, 10, seed=9, bg_hi=0.9)
+    boxes = boxes.numpy()
+    scores = (rng.random(8400, dtype=np.float32) * 2 - 1).astype(np.float32)
+    scores += np.arange(8400, dtype=np.float32) * 1e-7
+    for thr in (-0.5, 0.0, -2.0):
+        got = _gpu(boxes[None], scores[None], confidence_threshold=thr)[0]
+        want = no.select_nms(boxes, scores, conf_thr=thr).tolist()
+        assert got == want and len(want) > 0, thr
+
+
 def test_topk_and_keep_limits():
     boxes, scores = clustered_anchors(33600, 60, 30, seed=8, size=1280.0, bg_hi=0.7)
     boxes, scores = boxes.numpy(), scores.numpy()

@@ -109,7 +109,10 @@ def test_batch_parse_equals_per_image_reference_loop():
     assert [len(h) for h in got] == cnt.tolist()
     for i in range(B):
         want = reference_loop(out, i, caches[i])
-        assert len(det._parse_predictions(out, i, caches[i])) == len(want)
+        lo, hi = int(out["offsets"][i]), int(out["offsets"][i + 1])
+        one = det._parse_predictions(out["keep_boxes"][i, :hi - lo], out["keep_scores"][i, :hi - lo], out["params"][lo:hi],   # reference signature
+                                     dict(caches[i], _decoded=(out["vertices"][lo:hi], out["rotations"][lo:hi])))
+        assert len(one) == len(want) and all(np.array_equal(a.vertices_3d, b.vertices_3d) for a, b in zip(one, want))
         for a, b in zip(want, got[i]):
             assert tuple(int(v) for v in a.bbox) == tuple(int(v) for v in b.bbox)
             assert a.score == b.score and np.array_equal(a.vertices_3d, b.vertices_3d) and a.head_pose == b.head_pose
