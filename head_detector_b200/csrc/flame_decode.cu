@@ -140,11 +140,20 @@ __global__ void __launch_bounds__(kTileV* HG, HG == 1 ? 4 : 3) flame_decode_kern
   float* R_s = reinterpret_cast<float*>(js2_s + 3 * kL);                // [kHeads][9]
   float* st_s = R_s + kHeads * 9;                                       // [kHeads][8]: scale,tx,ty,tz,padx,pady,iscale
   for (int i = tid; i < 3 * kL; i += blockDim.x) js2_s[i] = a.c.js2[i];  // once per CTA (coalesced), reused by every item
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+  // items are ordered head-group-major and every CTA takes a CONTIGUOUS range of them, so that the per-head-group
+  // prologue (betas to fp64, Rodrigues, 6D rotation, jaw-joint regression: a 192..400-term dependent chain) runs once per
+  // head group a CTA touches instead of once per (vertex tile, head group)
+  const int per_cta = (n_items + gridDim.x - 1) / gridDim.x;
+  const int item_begin = blockIdx.x * per_cta, item_end = min(n_items, item_begin + per_cta);
+  int prologue_head0 = -1;
+  for (int item = item_begin; item < item_end; ++item) {
   const int head0 = (item / kVTiles) * kHeads;
   const int v0 = (item % kVTiles) * kTileV;
+  const bool fresh = head0 != prologue_head0;   // uniform across the CTA
+  prologue_head0 = head0;
 
   // ---- prologue: betas (fp64), per-head rotations
+  if (fresh) {
   for (int idx = tid; idx < lb * kHeads; idx += blockDim.x) {
     const int h = idx / lb, i = idx - h * lb;
     const int l = i < a.ns ? i : 300 + (i - a.ns);
@@ -163,7 +172,7 @@ __global__ void __launch_bounds__(kTileV* HG, HG == 1 ? 4 : 3) flame_decode_kern
       t[0] = p[409]; t[1] = p[410]; t[2] = p[411];
       sc = fmaxf(p[412], 1e-8f);
       if (a.xform) { xf[0] = a.xform[hg * 3]; xf[1] = a.xform[hg * 3 + 1]; xf[2] = a.xform[hg * 3 + 2]; }
-      if (a.rot && v0 == 0)
+      if (a.rot)   // (every CTA that starts on this head group writes the same values)
         for (int i = 0; i < 9; ++i) a.rot[static_cast<size_t>(hg) * 9 + i] = R[i];
     }
     for (int i = 0; i < 9; ++i) {
@@ -203,6 +212,7 @@ __global__ void __launch_bounds__(kTileV* HG, HG == 1 ? 4 : 3) flame_decode_kern
     const double o2 = j2 - (r[6] * j0 + r[7] * j1 + r[8] * j2);
     tj_s[tid * 3] = o0; tj_s[tid * 3 + 1] = o1; tj_s[tid * 3 + 2] = o2;
   }
+  }  // fresh head group
   // (visibility of tj_s to everyone is guaranteed by the __syncthreads inside the main loop)
 
   // ---- main loop: acc[h][k] = template + sum_i beta[h][i] * basis[i][v][k]

@@ -30,7 +30,7 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
 }
 
 // w: packed K-major weights [>= 48][32] bf16 (27 taps in (ky,kx,c) order + 5 zeros), bias [48] fp32
-__global__ void __launch_bounds__(256) stem_conv_kernel(const uint8_t* __restrict__ img, const __nv_bfloat16* __restrict__ w,
+__global__ void __launch_bounds__(256, 4) stem_conv_kernel(const uint8_t* __restrict__ img, const __nv_bfloat16* __restrict__ w,
                                                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int S,
                                                         int out_cstride, int relu) {
   __shared__ __align__(16) uint8_t tile[kStemIn * kStemRow];
@@ -42,12 +42,24 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const uint8_t* __restric
   const int oy0 = ty * kStemTile, ox0 = tx * kStemTile;
   const int iy0 = 2 * oy0 - 1, ix0 = 2 * ox0 - 1;
   const uint8_t* src = img + static_cast<size_t>(b) * S * S * 3;
-  for (int i = threadIdx.x; i < kStemIn * kStemRow; i += blockDim.x) {
-    const int r = i / kStemRow, c = i - r * kStemRow;
-    const int iy = iy0 + r, ix = ix0 + c / 3;
-    uint8_t v = 0;
-    if (c < kStemIn * 3 && iy >= 0 && iy < S && ix >= 0 && ix < S) v = __ldg(src + (static_cast<size_t>(iy) * S + ix0) * 3 + c);
-    tile[i] = v;
+  {
+    // all loads of a thread are issued before the first one is consumed (one memory latency per CTA, not thirteen)
+    constexpr int kLoads = (kStemIn * kStemRow + 255) / 256;
+    uint8_t v[kLoads];
+#pragma unroll
+    for (int q = 0; q < kLoads; ++q) {
+      const int i = threadIdx.x + q * 256;
+      const int r = i / kStemRow, c = i - r * kStemRow;
+      const int iy = iy0 + r, ix = ix0 + c / 3;
+      v[q] = 0;
+      if (i < kStemIn * kStemRow && c < kStemIn * 3 && iy >= 0 && iy < S && ix >= 0 && ix < S)
+        v[q] = __ldg(src + (static_cast<size_t>(iy) * S + ix0) * 3 + c);
+    }
+#pragma unroll
+    for (int q = 0; q < kLoads; ++q) {
+      const int i = threadIdx.x + q * 256;
+      if (i < kStemIn * kStemRow) tile[i] = v[q];
+    }
   }
   for (int i = threadIdx.x; i < kStemTile * kStemTile; i += blockDim.x) {   // channels 48..63 of the padded output
     *reinterpret_cast<uint4*>(&stage[i * kStemOutPitch + 48]) = make_uint4(0, 0, 0, 0);
@@ -120,7 +132,9 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const uint8_t* __restric
   }
   __syncthreads();
   // 256 pixels x 128 bytes, full lines
-  for (int i = threadIdx.x; i < kStemTile * kStemTile * 8; i += blockDim.x) {
+#pragma unroll
+  for (int q = 0; q < kStemTile * kStemTile * 8 / 256; ++q) {
+    const int i = threadIdx.x + q * 256;
     const int pix = i >> 3, c8 = i & 7;
     const int py = pix / kStemTile, px = pix - py * kStemTile;
     const uint4 v = *reinterpret_cast<const uint4*>(&stage[pix * kStemOutPitch + 8 * c8]);

@@ -13,11 +13,14 @@ from head_detector_b200.engine import Engine  # noqa: E402
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
     S = int(sys.argv[2]) if len(sys.argv) > 2 else 640
-    tag = sys.argv[3] if len(sys.argv) > 3 else "r1"
-    eng = Engine(arch.synthetic_weights(0), B, S)
+    tag = sys.argv[3] if len(sys.argv) > 3 else "r2"
+    flags = sys.argv[4:]
+    eng = Engine(arch.synthetic_weights(0), B, S, sparse_heads="dense" not in flags)
     eng.input.copy_(synth.synthetic_images(B, S, 0).cuda())
     boxes, scores = synth.engineered_heads(B, eng.A, S, 8, seed=7)
     eng.set_override(boxes.cuda(), scores.cuda())
+    if "untuned" not in flags:
+        eng.autotune(5)
     eng.profile(iters=2)
     rows = eng.profile(iters=10)
     tot = sum(t for _, t, _ in rows)
@@ -33,7 +36,8 @@ def main():
             extra = ""
             if op is not None and fl:
                 r = eng.plan.bufs[op.src[0]][0]
-                extra = f"k{op.k} s{op.stride} cin{op.src[2]:5d} cout{op.cout:5d} in{r:4d}"
+                c = eng.op_config(list(eng.plan.ops).index(op))
+                extra = f"k{op.k} s{op.stride} cin{op.src[2]:5d} cout{op.cout:5d} in{r:4d} mt{c['mt']} st{c['stages']} bn{c['block_n']} bk{c['bk']} tile{c['tw']}x{c['th']}"
             log(f"{label:28s} {t * 1e3:9.1f} us {fl / t / 1e9 if t > 0 else 0:8.1f} TF/s {100 * t / tot:5.1f}%  {extra}")
 
 
