@@ -10,3 +10,8 @@ import json
 d=json.loads(open("gpurun_out/r2_bench_1gpu_c.json").read().strip().splitlines()[-1])
 print(round(d["value"]), "img/s e2e", round(d["e2e"]["value"]), "frac_serial", round(d["roofline"]["frac_serial"],3), "frac_step", round(d["roofline"]["frac_step"],3), d["clocks"]["sm_mhz"])
 PY
+if [ -n "$NCU" ]; then
+  VGGHEADS_B200_SPARSE_HEADS=1 timeout 900 ncu --profile-from-start off --clock-control none --csv \
+    --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__cycles_active.avg,sm__cycles_elapsed.avg,l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed,lts__t_bytes.sum \
+    --log-file gpurun_out/r2_ncu_launches.csv python tools/ncu_target.py 64 tuned > gpurun_out/r2_ncu_target.log 2>&1; echo "ncu rc=$?"; wc -l gpurun_out/r2_ncu_launches.csv
+fi
