@@ -13,7 +13,7 @@ from head_detector_b200.engine import Engine  # noqa: E402
 
 B, S, heads = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 steps = int(sys.argv[4]) if len(sys.argv) > 4 else 10
-eng = Engine(arch.synthetic_weights(0), B, S)
+eng = Engine(arch.synthetic_weights(0), B, S, sparse_heads=True)
 eng.input.copy_(synth.synthetic_images(B, S, 0).cuda())
 boxes, scores = synth.engineered_heads(B, eng.A, S, heads, per_cluster=12 if S == 640 else 40, seed=7)
 eng.set_override(boxes.cuda(), scores.cuda())
