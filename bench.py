@@ -229,7 +229,6 @@ def parity_end_to_end(weights, batch=2):
     never reach 0.5): are the kept anchor ids those of `utils.nms` on the oracle's boxes / scores, and how far are the
     decoded vertices from the oracle's (bar of the metric: 1e-4 px)."""
     try:
-        import numpy as np
         import torch
 
         from head_detector_b200 import synth

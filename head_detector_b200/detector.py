@@ -22,7 +22,6 @@ from typing import Any, Dict, List, Optional, Tuple, Union
 import numpy as np
 import torch
 
-from . import arch  # noqa: F401
 from .detection_result import PredictionResult
 from .engine import Engine
 from .flame import FLAMELayer

@@ -2,9 +2,8 @@
 `PredictionResult.get_pncc()` (reference: head_detector/pncc_processor.py:59-73 over the CPU rasteriser Sim3DR) and
 `refined_head_bbox` (head_detector/utils.py:26-35).  The tables PNCCProcessor.__init__ rebuilds for every
 PredictionResult in the reference (a Python filter over 9976 faces, ~0.09 s) are precomputed assets here and uploaded once."""
-import ctypes as C
 import os
-from typing import List, Sequence
+from typing import Sequence
 
 import numpy as np
 import torch

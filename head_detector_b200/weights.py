@@ -21,7 +21,7 @@ names differ fails loudly with the list of missing / unexpected keys instead of 
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Tuple
 
 import torch
 

@@ -234,7 +234,7 @@ def pncc_case():
 
     subprocess.run(["make", "-C", HERE, "_ref/libsim3dr_ref.so"], check=True, capture_output=True)
     from head_detector.detection_result import PredictionResult
-    from head_detector.head_info import Bbox, FlameParams, HeadMetadata
+    from head_detector.head_info import FlameParams, HeadMetadata
     from head_detector.utils import calculate_rpy, refined_head_bbox
 
     g = np.load(os.path.join(OUT, "flame_ref_heads.npz"))

@@ -20,8 +20,6 @@ from __future__ import annotations
 import math
 import os
 import sys
-from typing import Dict, List
-
 import torch
 import torch.nn.functional as F
 from torch import nn

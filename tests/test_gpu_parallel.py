@@ -6,7 +6,6 @@ import socket
 import sys
 import traceback
 
-import numpy as np
 import pytest
 import torch
 

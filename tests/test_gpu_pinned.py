@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import net_oracle, nms_oracle, sg_net
+from oracle import net_oracle, sg_net
 from oracle.make_golden import DETECTOR_SEED, HEADS_SEED, detector_image, detector_net, heads_feats
 
 pytestmark = pytest.mark.gpu
