@@ -34,7 +34,7 @@ constexpr int kL = 400;
 constexpr int kTileV = 128;
 constexpr int kHPT = 8;   // heads per thread
 constexpr int kLc = 8;    // coefficients per pipeline stage
-constexpr int kNS = 4;    // pipeline stages of the basis stream
+constexpr int kNS = 3;    // pipeline stages of the basis stream (3 x 12 KB: three CTAs per SM fit, ncu: the kernel is latency-, not bandwidth-bound)
 constexpr int kNPose = 9; // live pose-corrective rows (jaw joint only)
 constexpr int kParams = 413;
 
@@ -136,10 +136,11 @@ __global__ void __launch_bounds__(kTileV* HG, HG == 1 ? 4 : 3) flame_decode_kern
   double* beta_s = reinterpret_cast<double*>(sd_s + kNS * kLc * kTileV * 3);  // [lt_pad][kHeads]
   double* tj_s = beta_s + static_cast<size_t>(lt_pad) * kHeads;         // [kHeads][3]
   double* r2_s = tj_s + kHeads * 3;                                     // [kHeads][9]
-  double* js2_s = r2_s + kHeads * 9;                                    // [3][400] jaw-joint regressor x shape basis
-  float* R_s = reinterpret_cast<float*>(js2_s + 3 * kL);                // [kHeads][9]
+  float* R_s = reinterpret_cast<float*>(r2_s + kHeads * 9);             // [kHeads][9]
   float* st_s = R_s + kHeads * 9;                                       // [kHeads][8]: scale,tx,ty,tz,padx,pady,iscale
-  for (int i = tid; i < 3 * kL; i += blockDim.x) js2_s[i] = a.c.js2[i];  // once per CTA (coalesced), reused by every item
+  // [3][400] jaw-joint regressor x shape basis: only read in the prologue, so it borrows the (idle) basis stage buffers
+  double* js2_s = reinterpret_cast<double*>(sd_s);
+  static_assert(3 * kL * sizeof(double) <= kNS * kLc * kTileV * 3 * sizeof(float), "js2 must fit the stage buffers");
   // items are ordered head-group-major and every CTA takes a CONTIGUOUS range of them, so that the per-head-group
   // prologue (betas to fp64, Rodrigues, 6D rotation, jaw-joint regression: a 192..400-term dependent chain) runs once per
   // head group a CTA touches instead of once per (vertex tile, head group)
@@ -154,6 +155,7 @@ __global__ void __launch_bounds__(kTileV* HG, HG == 1 ? 4 : 3) flame_decode_kern
 
   // ---- prologue: betas (fp64), per-head rotations
   if (fresh) {
+  for (int i = tid; i < 3 * kL; i += blockDim.x) js2_s[i] = a.c.js2[i];  // (the previous item's last basis reads are behind a barrier)
   for (int idx = tid; idx < lb * kHeads; idx += blockDim.x) {
     const int h = idx / lb, i = idx - h * lb;
     const int l = i < a.ns ? i : 300 + (i - a.ns);
@@ -321,7 +323,7 @@ struct FlameModel {
 
 static size_t flame_smem_bytes(int heads, int lt_pad) {
   return sizeof(float) * (kNS * kLc * kTileV * 3) +
-         sizeof(double) * (static_cast<size_t>(lt_pad) * heads + heads * 3 + heads * 9 + 3 * kL) +
+         sizeof(double) * (static_cast<size_t>(lt_pad) * heads + heads * 3 + heads * 9) +
          sizeof(float) * (heads * 9 + heads * 8);
 }
 
