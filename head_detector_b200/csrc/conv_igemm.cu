@@ -436,7 +436,7 @@ int conv_make_tensor_maps(ConvLaunch& L, const void* in_base, int in_C, int in_H
     cuuint64_t dims[4] = {(cuuint64_t)in_C, (cuuint64_t)in_W, (cuuint64_t)in_H, (cuuint64_t)L.B};
     cuuint64_t strides[3] = {(cuuint64_t)in_C * 2, (cuuint64_t)in_W * in_C * 2, (cuuint64_t)in_H * in_W * in_C * 2};
     cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(L.tw * L.stride), (cuuint32_t)(L.th * L.stride), 1};
-    if (L.swap && L.xr) box[2] = (cuuint32_t)(L.th + 2);  // tap-reuse variant: one halo row above and below
+    if (L.swap && L.xr) box[2] = (cuuint32_t)(L.pair ? L.th / 2 + 2 : L.th + 2);  // tap-reuse variant: one halo row above and below (CTA pairs: half a tile each)
     cuuint32_t estr[4] = {1, (cuuint32_t)L.stride, (cuuint32_t)L.stride, 1};
     CUresult r = enc(&L.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in_base), dims, strides, box,
                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,

@@ -47,6 +47,7 @@ struct ConvLaunch {
   int xr, xslots;                // swapped kernel, 3x3 stride 1: pixel tile + halo rows fetched once per column shift
                                  // and reused by the three row taps (xslots = pixel-tile ring depth; `stages` = weight ring)
   int cluster;                   // swapped kernel: 1, or 2 = CTA pairs share every weight k-block (each fetches half, TMA multicast)
+  int pair;                      // swapped tap-reuse kernel: 1 = CTA pairs run one cta_group::2 MMA (M = 256 = two channel groups) per pixel tile
   int acc_stages, n_tiles, num_items;  // TMEM accumulator stages (1|2), N tiles, work items (persistent CTAs)
   int split;                     // normal kernel, parity mode: store y as bf16 terms h|m|l in six planes per 32-channel granule
 };

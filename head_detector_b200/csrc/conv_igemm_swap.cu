@@ -37,6 +37,16 @@
 // is the bytes each SM ingests, which a multicast does not reduce.  Kept, parity-tested, as the cluster
 // plumbing (work-item mapping per pair, cluster barriers, multicast commits) cta_group::2 MMA pairs need.
 //
+// Pair variant (`p.pair`, template PAIR; 3x3 stride-1 layers with an even number of 128-channel groups): two CTAs of a
+// cluster run ONE tcgen05.mma.cta_group::2 with M = 256 - CTA r holds the 128 weight rows of channel group 2g + r and gets
+// their accumulator rows in its own TMEM - over ONE pixel tile whose N-side operand is split between them: CTA r stages
+// only the upper / lower half of the tile (th/2 + 2 rows with halo) and the hardware reads N/2 rows from each CTA's
+// shared memory.  Per SM that halves the pixel-tile fills and the MMA's pixel-operand reads: 160 -> 119 B/clk through the
+// shared-memory port for a 256-channel layer, which is what bounded these layers at 78-80 % tensor-active.
+// Both CTAs issue their own TMA loads but credit the byte counts to the LEADER's full barriers; the leader issues the
+// MMAs and releases slots / publishes accumulators with multicast commits to both CTAs; the peer's epilogue warps
+// hand the accumulator stage back by arriving on the leader's barrier through the cluster address space.
+//
 // Everything else matches conv_igemm.cu: persistent CTAs, TMA (4-D pixel box with OOB zero fill =
 // padding, traversal stride = conv stride; 2-D weight box), mbarrier ring, double-buffered TMEM.
 #include <cstdio>
@@ -50,8 +60,9 @@ namespace vgh {
 constexpr int kSwapEpiWarps = 8;
 constexpr int kSwapThreads = 64 + 32 * kSwapEpiWarps;
 
-template <int BK, bool XR>
+template <int BK, bool XR, bool PAIR = false>
 __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const __grid_constant__ ConvLaunch p) {
+  static_assert(!PAIR || XR, "CTA pairs are built for the tap-reuse variant");
   constexpr uint32_t kRowBytes = BK * 2;
   constexpr uint32_t kWBytes = 128 * kRowBytes;  // weight slot: 128 cout rows (the MMA M)
   // only the group's own gw rows are fetched; the MMA still reads 128 rows, the rest is whatever the slot held -
@@ -61,7 +72,8 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int npix = p.tw * p.th;                                   // UMMA N (multiple of 16, <= 256)
   // pixel tile bytes; XR: the tile carries one halo row above and below
-  const uint32_t x_bytes = static_cast<uint32_t>(XR ? p.tw * (p.th + 2) : npix) * kRowBytes;
+  // (PAIR: this CTA's half of the tile, th/2 rows + halo)
+  const uint32_t x_bytes = static_cast<uint32_t>(PAIR ? p.tw * (p.th / 2 + 2) : XR ? p.tw * (p.th + 2) : npix) * kRowBytes;
   const uint32_t x_slot = (x_bytes + 1023u) & ~1023u;
   const int ks = XR ? 1 : p.ks;                                     // k-blocks per pipeline stage (one barrier round trip)
   const int x_slots = XR ? p.xslots : p.stages * ks;               // XR: the pixel tiles have their own (shallower) ring
@@ -88,17 +100,21 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
   // Work items: a cluster (1 or 2 CTAs) walks (tile group of n_cl pixel tiles, channel group); CTA r of the
   // cluster takes tile r of the group.  With n_cl == 1 this is item = tile * ngroups + group as before.
   // The counts are set after the PDL wait: survivor-patch launches read their live height from device memory.
-  const int n_cl = p.cluster;
-  const uint32_t cta_rank = n_cl > 1 ? cluster_ctarank() : 0u;
-  const int cl_id = blockIdx.x / n_cl, n_cls = gridDim.x / n_cl;
+  const int n_cl = PAIR ? 1 : p.cluster;   // weight-multicast clusters (PAIR uses the cluster for the MMA instead)
+  constexpr int kCtas = PAIR ? 2 : 1;
+  const uint32_t cta_rank = (n_cl > 1 || PAIR) ? cluster_ctarank() : 0u;
+  const bool leader = !PAIR || cta_rank == 0u;
+  const int cl_id = blockIdx.x / (PAIR ? 2 : n_cl), n_cls = gridDim.x / (PAIR ? 2 : n_cl);
   int tiles_per_img = p.tiles_x * p.tiles_y;
   int total_tiles = tiles_per_img * p.B;
-  int n_citems = ((total_tiles + n_cl - 1) / n_cl) * p.ngroups;
+  const int item_groups = PAIR ? p.ngroups / 2 : p.ngroups;   // PAIR: one item = pixel tile x PAIR of channel groups
+  int n_citems = ((total_tiles + n_cl - 1) / n_cl) * item_groups;
   // -> tile (clamped; `valid` false for the filler tile of an odd tile count: computed, never stored), group base
   auto item_tile = [&](int ci, int& tile, int& n_base) -> bool {
-    const int tg = ci / p.ngroups;
-    n_base = (ci - tg * p.ngroups) * p.gw;
-    tile = tg * n_cl + static_cast<int>(cta_rank);
+    const int tg = ci / item_groups;
+    const int g = ci - tg * item_groups;
+    n_base = (PAIR ? 2 * g + static_cast<int>(cta_rank) : g) * p.gw;
+    tile = PAIR ? tg : tg * n_cl + static_cast<int>(cta_rank);
     const bool valid = tile < total_tiles;
     if (!valid) tile = total_tiles - 1;
     return valid;
@@ -114,7 +130,7 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar + 8 * a, 1);
-      mbar_init(tmem_empty_bar + 8 * a, kSwapEpiWarps);
+      mbar_init(tmem_empty_bar + 8 * a, kSwapEpiWarps * kCtas);  // PAIR: the leader's barrier also collects the peer's epilogue warps
     }
     mbar_init(res_full_bar, 1);
     mbar_init(res_full_bar + 8, 1);
@@ -127,13 +143,18 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc_dyn(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_dyn_2cta(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+      tmem_relinquish_2cta();
+    } else {
+      tmem_alloc_dyn(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (n_cl > 1) cluster_sync_all();  // the peer's barriers exist before anything is multicast to / arrives on them
+  if (n_cl > 1 || PAIR) cluster_sync_all();  // the peer's barriers exist before anything is multicast to / arrives on them
   uint32_t tmem_acc;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_acc) : "r"(tmem_slot));
   // everything above overlapped the previous kernel's tail (PDL); its outputs are needed from here on
@@ -143,7 +164,7 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
     const int rows = min(__ldg(p.dyn_rows), p.Ho);
     tiles_per_img = p.tiles_x * ((rows + p.th - 1) / p.th);
     total_tiles = tiles_per_img * p.B;
-    n_citems = ((total_tiles + n_cl - 1) / n_cl) * p.ngroups;
+    n_citems = ((total_tiles + n_cl - 1) / n_cl) * item_groups;
   }
 
   const int cblks = p.cin / BK;
@@ -171,7 +192,30 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
         const int t_in = tile - b_img * tiles_per_img;
         const int tyi = t_in / p.tiles_x;
         const int h0 = tyi * p.th, w0 = (t_in - tyi * p.tiles_x) * p.tw;
-        if constexpr (XR) {
+        if constexpr (PAIR) {
+          // both CTAs fetch their own operand halves; the LEADER's full barriers count the bytes of both
+          const int hh = h0 + static_cast<int>(cta_rank) * (p.th / 2) - 1;
+          for (int cb = 0; cb < cblks; ++cb) {
+            for (int dx = 0; dx < 3; ++dx) {
+              mbar_wait(xempty_bar + 8 * xs, xphase ^ 1);
+              if (leader) mbar_arrive_expect_tx(xfull_bar + 8 * xs, 2 * x_bytes);
+              tma_load_4d_2cta(x_base + xs * x_slot, &p.tmA, map_to_cta(xfull_bar + 8 * xs, 0), p.cin_off + cb * BK, w0 + dx - 1, hh, b_img);
+              if (++xs == p.xslots) {
+                xs = 0;
+                xphase ^= 1;
+              }
+              for (int dy = 0; dy < 3; ++dy) {
+                mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                if (leader) mbar_arrive_expect_tx(full_bar + 8 * stage, 2 * w_tx);
+                tma_load_2d_2cta(w_base + stage * kWBytes, &p.tmB, map_to_cta(full_bar + 8 * stage, 0), (dy * 3 + dx) * p.cin + cb * BK, n_base);
+                if (++stage == p.stages) {
+                  stage = 0;
+                  phase ^= 1;
+                }
+              }
+            }
+          }
+        } else if constexpr (XR) {
           // pixel tile (with halo rows) once per (cin block, dx); weights tap by tap
           for (int cb = 0; cb < cblks; ++cb) {
             for (int dx = 0; dx < 3; ++dx) {
@@ -219,9 +263,9 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      const uint32_t idesc = umma_idesc_bf16(128, static_cast<uint32_t>(npix));
+    if (lane == 0 && leader) {
+      // ===================== MMA issuer (PAIR: the leader CTA, for both) =====================
+      const uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, static_cast<uint32_t>(npix));
       int stage = 0, xs = 0;
       uint32_t phase = 0, xphase = 0;
       int acc = 0;
@@ -243,16 +287,20 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
               const uint64_t x_desc = umma_smem_desc(x_base + xs * x_slot + dy * dy_bytes, kRowBytes);
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) {
-                umma_bf16(d, w_desc + 2 * k, x_desc + 2 * k, idesc, accumulate);
+                if (PAIR) umma_bf16_2cta(d, w_desc + 2 * k, x_desc + 2 * k, idesc, accumulate);
+                else umma_bf16(d, w_desc + 2 * k, x_desc + 2 * k, idesc, accumulate);
                 accumulate = 1u;
               }
-              if (n_cl > 1) umma_commit_mc(empty_bar + 8 * stage, mc_mask); else umma_commit(empty_bar + 8 * stage);
+              if (PAIR) umma_commit_2cta_mc(empty_bar + 8 * stage, 3);
+              else if (n_cl > 1) umma_commit_mc(empty_bar + 8 * stage, mc_mask);
+              else umma_commit(empty_bar + 8 * stage);
               if (++stage == p.stages) {
                 stage = 0;
                 phase ^= 1;
               }
             }
-            umma_commit(xempty_bar + 8 * xs);  // all three row taps of this pixel tile have been issued
+            // all three row taps of this pixel tile have been issued
+            if (PAIR) umma_commit_2cta_mc(xempty_bar + 8 * xs, 3); else umma_commit(xempty_bar + 8 * xs);
             if (++xs == p.xslots) {
               xs = 0;
               xphase ^= 1;
@@ -276,7 +324,7 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
             }
           }
         }
-        umma_commit(tmem_full_bar + 8 * acc);
+        if (PAIR) umma_commit_2cta_mc(tmem_full_bar + 8 * acc, 3); else umma_commit(tmem_full_bar + 8 * acc);
         if (++acc == p.acc_stages) {
           acc = 0;
           acc_phase ^= 1;
@@ -292,7 +340,7 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
     const bool ch_ok = ch < gw;
     const int n_chunks = npix >> 4;
     const bool has_res = p.res != nullptr;
-    const bool leader = (ew == 0 && lane == 0);
+    const bool epi_lead = (ew == 0 && lane == 0);
     uint8_t* stile0 = smem_raw + (stage_base - smem_u32(smem_raw));
     // cluster work item -> tile origin, channel-group base; false for a filler tile (computed, not stored)
     auto item_coords = [&](int item, int& b_img, int& h0, int& w0, int& n_base) -> bool {
@@ -305,14 +353,14 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
       w0 = (t_in - tyi * p.tiles_x) * p.tw;
       return valid;
     };
-    if (has_res && leader && cl_id < n_citems) {  // residual tile of the first item -> buffer 0
+    if (has_res && epi_lead && cl_id < n_citems) {  // residual tile of the first item -> buffer 0
       int b_img, h0, w0, nb0;
       item_coords(cl_id, b_img, h0, w0, nb0);
       tma_prefetch_desc(&p.tmRes);
       mbar_arrive_expect_tx(res_full_bar, stage_bytes);
       tma_load_4d(stage_base, &p.tmRes, res_full_bar, p.res_coff + nb0, w0, h0, b_img);
     }
-    if (leader) tma_prefetch_desc(&p.tmOut);
+    if (epi_lead) tma_prefetch_desc(&p.tmOut);
     int acc = 0, sb = 0;
     uint32_t acc_phase = 0, res_phase[2] = {0, 0};
     for (int item = cl_id; item < n_citems; item += n_cls) {
@@ -355,12 +403,15 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
       // TMEM drained by this warp -> MMA may reuse the accumulator stage
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty_bar + 8 * acc);
+      if (lane == 0) {
+        if (PAIR && !leader) mbar_arrive_cluster(map_to_cta(tmem_empty_bar + 8 * acc, 0));   // the leader's MMA warp waits for both CTAs
+        else mbar_arrive(tmem_empty_bar + 8 * acc);
+      }
       // hand the finished tile to the TMA unit
       fence_proxy_async();
       named_bar_sync(1, 32 * kSwapEpiWarps);
       const int nsb = stg_bufs == 2 ? (sb ^ 1) : sb;
-      if (leader) {
+      if (epi_lead) {
         if (valid) tma_store_4d(&p.tmOut, stage_base + sb * stage_slot, p.out_coff + n_base, w0, h0, b_img);
         tma_store_commit();
         // the tile the NEXT item writes must have been read out by its previous store
@@ -380,14 +431,16 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
         acc_phase ^= 1;
       }
     }
-    if (leader) tma_store_wait_read();  // shared memory must outlive the last store's read
+    if (epi_lead) tma_store_wait_read();  // shared memory must outlive the last store's read
   }
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // both CTAs are done with the pair's MMAs / TMEM / barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc_dyn(tmem_acc, static_cast<uint32_t>(p.tmem_cols));
+    if (PAIR) tmem_dealloc_dyn_2cta(tmem_acc, static_cast<uint32_t>(p.tmem_cols));
+    else tmem_dealloc_dyn(tmem_acc, static_cast<uint32_t>(p.tmem_cols));
   }
   // the peer's last slot releases land on this CTA's barriers: shared memory must outlive them
   if (n_cl > 1) cluster_sync_all();
@@ -396,26 +449,26 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
 size_t conv_swap_smem_bytes(const ConvLaunch& L, int bk) {
   const size_t staging = (static_cast<size_t>(L.tw * L.th) * L.gw * (L.out_fp32 ? 4 : 2) + 1023) & ~static_cast<size_t>(1023);
   if (L.xr) {
-    const size_t x_slot = (static_cast<size_t>(L.tw * (L.th + 2)) * bk * 2 + 1023) & ~static_cast<size_t>(1023);
+    const size_t x_slot = (static_cast<size_t>(L.tw * (L.pair ? L.th / 2 + 2 : L.th + 2)) * bk * 2 + 1023) & ~static_cast<size_t>(1023);
     return 1024 + static_cast<size_t>(L.stages) * 128 * bk * 2 + L.xslots * x_slot + L.stg_bufs * staging + 16 * L.stages + 256;
   }
   const size_t x_slot = (static_cast<size_t>(L.tw * L.th) * bk * 2 + 1023) & ~static_cast<size_t>(1023);
   return 1024 + static_cast<size_t>(L.stages) * L.ks * (128 * bk * 2 + x_slot) + L.stg_bufs * staging + 16 * L.stages + 256;
 }
 
-template <int BK, bool XR>
+template <int BK, bool XR, bool PAIR = false>
 static int launch_swap_t(const ConvLaunch& L, int sms, cudaStream_t stream, char* err, size_t errlen) {
   static SmemOptIn opt_in;
   const size_t smem = conv_swap_smem_bytes(L, BK);
   {
-    cudaError_t e = ensure_dynamic_smem(conv_igemm_swap_kernel<BK, XR>, opt_in, smem);
+    cudaError_t e = ensure_dynamic_smem(conv_igemm_swap_kernel<BK, XR, PAIR>, opt_in, smem);
     if (e != cudaSuccess) {
       snprintf(err, errlen, "swap conv: set smem %zu failed: %s", smem, cudaGetErrorString(e));
       return 4;
     }
   }
   cudaLaunchConfig_t cfg{};
-  const int n_cl = L.cluster > 1 ? L.cluster : 1;
+  const int n_cl = PAIR ? 2 : (L.cluster > 1 ? L.cluster : 1);
   int grid = L.num_items < sms ? L.num_items : sms;  // num_items counts CTA-level items (cluster items x cluster size)
   grid -= grid % n_cl;
   cfg.gridDim = dim3(grid);
@@ -438,7 +491,7 @@ static int launch_swap_t(const ConvLaunch& L, int sms, cudaStream_t stream, char
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm_swap_kernel<BK, XR>, L);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm_swap_kernel<BK, XR, PAIR>, L);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(err, errlen, "swap conv launch failed: %s", cudaGetErrorString(e));
@@ -457,6 +510,13 @@ int conv_swap_launch(const ConvLaunch& L, int bk, int sms, cudaStream_t stream, 
       snprintf(err, errlen, "swap conv: launch not eligible for the tap-reuse variant (taps %d stride %d tile %dx%d xslots %d stages %d)",
                L.ntaps, L.stride, L.tw, L.th, L.xslots, L.stages);
       return 7;
+    }
+    if (L.pair) {
+      if (bk != 64 || L.gw != 128 || L.ngroups % 2 || L.th % 2 || L.cluster != 1 || L.dyn_rows != nullptr || (L.tw * L.th) % 32) {
+        snprintf(err, errlen, "swap conv: launch not eligible for CTA pairs (bk %d, group width %d, groups %d, tile %dx%d)", bk, L.gw, L.ngroups, L.tw, L.th);
+        return 7;
+      }
+      return launch_swap_t<64, true, true>(L, sms, stream, err, errlen);
     }
     if (bk == 64) return launch_swap_t<64, true>(L, sms, stream, err, errlen);
     if (bk == 32) return launch_swap_t<32, true>(L, sms, stream, err, errlen);

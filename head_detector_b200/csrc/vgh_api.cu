@@ -118,6 +118,7 @@ struct OpRt {
   int cfg_tail = 1;                                           // normal kernel: pack left-over rows across images
   int cfg_xr = -1, cfg_xslots = 0;                            // swapped kernel: tap-reuse variant (-1 = default), pixel ring depth
   int cfg_cluster = -1;                                       // swapped kernel: CTA pairs sharing the weight stream (-1 = default)
+  int cfg_pair = -1;                                          // swapped tap-reuse kernel: cta_group::2 MMA pairs (-1 = default)
 };
 
 struct vgh_detector {
@@ -262,6 +263,12 @@ static int cluster_default() {
   const char* e = getenv("VGGHEADS_B200_CLUSTER");
   return (e && e[0] == '1') ? 1 : 0;
 }
+// cta_group::2 MMA pairs (conv_igemm_swap.cu, PAIR): VGGHEADS_B200_PAIR = 0 (never) | 1 (default: wherever eligible; the
+// autotuner keeps whichever of pair / single measures faster per layer)
+static int pair_default() {
+  const char* e = getenv("VGGHEADS_B200_PAIR");
+  return (e && e[0] == '0') ? 0 : 1;
+}
 // test aid: VGGHEADS_B200_SWAP=1 makes the un-tuned heuristic pick the swapped kernel for every eligible op
 // (by default only large maps with Cout <= 128 do), so that small parity cases exercise it everywhere
 static bool swap_forced() {
@@ -309,8 +316,12 @@ static int build_conv(vgh_detector* d, OpRt& o) {
   L.xr = (L.swap && xr_eligible(q, ob)) ? (o.cfg_xr >= 0 ? o.cfg_xr : xr_default()) : 0;
   // pairs need a group width whose halves are whole 8-row swizzle atoms
   L.cluster = (L.swap && L.gw % 16 == 0 && (o.cfg_cluster >= 0 ? o.cfg_cluster : cluster_default())) ? 2 : 1;
+  // CTA pairs: two 128-channel groups per MMA; needs whole 64-channel K blocks and an even tile height (half a tile per CTA)
+  const bool pair_ok = L.xr && !patch_op && L.gw == 128 && L.ngroups % 2 == 0 && o.bk == 64 && L.cluster == 1;
+  L.pair = (pair_ok && (o.cfg_pair >= 0 ? o.cfg_pair : pair_default())) ? 1 : 0;
   if (o.cfg_tw > 0) { L.tw = o.cfg_tw; L.th = o.cfg_th; }
   else if (L.xr) pick_tile_swap_xr(L.Ho, L.Wo, L.tw, L.th);
+  if (L.pair && (L.th % 2 || (L.tw * L.th) % 32)) L.pair = 0;
   else if (L.swap) pick_tile_swap(L.Ho, L.Wo, L.tw, L.th);
   else pick_tile(L.Ho, L.Wo, d->B, o.cfg_tail != 0, L.tw, L.th);
   if (L.xr && L.tw % 8) return fail(2, "tap-reuse tiles must be a multiple of 8 pixels wide");
@@ -368,7 +379,7 @@ static int build_conv(vgh_detector* d, OpRt& o) {
   L.mt = L.swap ? 1 : (o.cfg_mt > 0 ? o.cfg_mt : conv_default_mt(L.block_n));
   if (L.swap && L.xr) {
     // two rings: pixel tiles with halo rows (xslots deep) and weight k-blocks (`stages` deep)
-    const int x_slot = (L.tw * (L.th + 2) * o.bk * 2 + 1023) & ~1023;
+    const int x_slot = (L.tw * (L.pair ? L.th / 2 + 2 : L.th + 2) * o.bk * 2 + 1023) & ~1023;
     const int w_bytes = 128 * o.bk * 2;
     const int staging = (L.tw * L.th * L.gw * (ob.fp32 ? 4 : 2) + 1023) & ~1023;
     const int budget = 224 * 1024 - staging;
@@ -720,7 +731,7 @@ extern "C" int vgh_detector_autotune(vgh_detector* d, int iters, void* stream) {
     float best = 1e30f;
     int best_mt = 0, best_st = 0, best_swap = 0, best_tw = 0, best_th = 0, best_ks = 1;
     const int bn = o.L.block_n;
-    int best_xr = 0, best_xs = 0, best_cl = 0;
+    int best_xr = 0, best_xs = 0, best_cl = 0, best_pr = 0;
     if (xr_eligible(o.d, d->bufs[o.d.out_buf]) && xr_default()) {
       // candidate tiles: every admissible shape ranked by a coarse cost model - waves of work items over the SMs
       // x (MMA columns + a share for the pixel rows each item ingests + a fixed per-item cost) - and the best six
@@ -752,11 +763,11 @@ extern "C" int vgh_detector_autotune(vgh_detector* d, int iters, void* stream) {
       }
       for (int ci = 0; ci < n_cand; ++ci) {
         const int ptw = cands[ci].tw, pth = cands[ci].th;
-        for (int xs : {2, 3}) for (int cl = 0; cl <= cluster_default(); ++cl) {
+        for (int xs : {2, 3}) for (int cl = 0; cl <= cluster_default(); ++cl) for (int pr = 0; pr <= pair_default(); ++pr) {
           OpRt t = o;
-          t.cfg_ks = 1; t.cfg_swap = 1; t.cfg_mt = 0; t.cfg_stages = 0; t.cfg_xr = 1; t.cfg_xslots = xs; t.cfg_cluster = cl;
+          t.cfg_ks = 1; t.cfg_swap = 1; t.cfg_mt = 0; t.cfg_stages = 0; t.cfg_xr = 1; t.cfg_xslots = xs; t.cfg_cluster = cl; t.cfg_pair = pr;
           t.cfg_tw = ptw; t.cfg_th = pth;
-          if (build_conv(d, t) || t.L.xslots != xs || t.L.cluster != cl + 1 || conv_launch(t.L, t.bk, s)) continue;
+          if (build_conv(d, t) || t.L.xslots != xs || t.L.cluster != cl + 1 || t.L.pair != pr || conv_launch(t.L, t.bk, s)) continue;
           float ms = 1e30f;
           for (int rep = 0; rep < 2; ++rep) {
             cudaEventRecord(e0, s);
@@ -767,14 +778,14 @@ extern "C" int vgh_detector_autotune(vgh_detector* d, int iters, void* stream) {
             cudaEventElapsedTime(&m, e0, e1);
             if (m < ms) ms = m;
           }
-          if (ms < best) { best = ms; best_swap = 1; best_mt = 1; best_st = 0; best_tw = t.cfg_tw; best_th = t.cfg_th; best_ks = 1; best_xr = 1; best_xs = xs; best_cl = cl; }
+          if (ms < best) { best = ms; best_swap = 1; best_mt = 1; best_st = 0; best_tw = t.cfg_tw; best_th = t.cfg_th; best_ks = 1; best_xr = 1; best_xs = xs; best_cl = cl; best_pr = pr; }
         }
       }
     }
     if (swap_eligible(o.d, d->bufs[o.d.out_buf])) {
       for (int max_px : {256, 192, 128}) for (int cl = 0; cl <= cluster_default(); ++cl) {  // pixel-tile size trades MMA width against pipeline depth
         OpRt t = o;
-        t.cfg_ks = 1; t.cfg_xr = 0; t.cfg_cluster = cl;
+        t.cfg_ks = 1; t.cfg_xr = 0; t.cfg_cluster = cl; t.cfg_pair = 0;
         t.cfg_swap = 1; t.cfg_mt = 0; t.cfg_stages = 0;
         pick_tile_swap(o.L.Ho, o.L.Wo, t.cfg_tw, t.cfg_th, max_px);
         if (max_px != 256 && t.cfg_tw * t.cfg_th > max_px) continue;
@@ -816,7 +827,7 @@ extern "C" int vgh_detector_autotune(vgh_detector* d, int iters, void* stream) {
           cudaEventElapsedTime(&m, e0, e1);
           if (m < ms) ms = m;
         }
-        if (ms < best) { best = ms; best_mt = mt; best_st = st; best_swap = 0; best_xr = 0; }
+        if (ms < best) { best = ms; best_mt = mt; best_st = st; best_swap = 0; best_xr = 0; best_pr = 0; }
       }
     }
     if (best_mt) {
@@ -828,6 +839,7 @@ extern "C" int vgh_detector_autotune(vgh_detector* d, int iters, void* stream) {
       o.cfg_stages = best_st;
       o.cfg_xr = best_swap ? best_xr : 0;
       o.cfg_cluster = best_swap ? best_cl : 0;
+      o.cfg_pair = best_xr ? best_pr : 0;
       o.cfg_xslots = best_xr ? best_xs : 0;
       int rc = build_conv(d, o);
       if (rc) return rc;
@@ -842,7 +854,7 @@ extern "C" int vgh_detector_autotune(vgh_detector* d, int iters, void* stream) {
 extern "C" int vgh_detector_op_config(const vgh_detector* d, int op, int32_t* out6) {
   if (!d || op < 0 || op >= (int)d->ops.size() || !out6) return fail(1, "bad argument");
   const OpRt& o = d->ops[op];
-  out6[0] = o.L.swap ? -(o.L.ks + 10 * (o.L.cluster - 1)) : o.L.mt;  // swapped: -ks, -1x = CTA pairs (weight multicast)
+  out6[0] = o.L.swap ? -(o.L.ks + 10 * (o.L.cluster - 1) + 20 * o.L.pair) : o.L.mt;  // swapped: -ks, -1x = weight-multicast pairs, -2x = cta_group::2 MMA pairs
   out6[1] = (o.L.swap && o.L.xr) ? 100 * o.L.xslots + o.L.stages : o.L.stages;  // tap reuse: 100*pixel slots + weight slots
   out6[2] = o.L.block_n; out6[3] = o.bk; out6[4] = o.L.tw; out6[5] = o.L.th;
   return 0;
