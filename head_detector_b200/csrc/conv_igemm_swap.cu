@@ -512,7 +512,7 @@ int conv_swap_launch(const ConvLaunch& L, int bk, int sms, cudaStream_t stream, 
       return 7;
     }
     if (L.pair) {
-      if (bk != 64 || L.gw != 128 || L.ngroups % 2 || L.th % 2 || L.cluster != 1 || L.dyn_rows != nullptr || (L.tw * L.th) % 32) {
+      if (bk != 64 || L.gw != 128 || L.ngroups % 2 || L.th % 2 || L.cluster != 1 || L.dyn_rows != nullptr || (L.tw * L.th) % 16) {
         snprintf(err, errlen, "swap conv: launch not eligible for CTA pairs (bk %d, group width %d, groups %d, tile %dx%d)", bk, L.gw, L.ngroups, L.tw, L.th);
         return 7;
       }

@@ -321,9 +321,10 @@ static int build_conv(vgh_detector* d, OpRt& o) {
   L.pair = (pair_ok && (o.cfg_pair >= 0 ? o.cfg_pair : pair_default())) ? 1 : 0;
   if (o.cfg_tw > 0) { L.tw = o.cfg_tw; L.th = o.cfg_th; }
   else if (L.xr) pick_tile_swap_xr(L.Ho, L.Wo, L.tw, L.th);
-  if (L.pair && (L.th % 2 || (L.tw * L.th) % 32)) L.pair = 0;
   else if (L.swap) pick_tile_swap(L.Ho, L.Wo, L.tw, L.th);
   else pick_tile(L.Ho, L.Wo, d->B, o.cfg_tail != 0, L.tw, L.th);
+  if (L.pair && o.cfg_tw <= 0 && L.th % 2 && L.th > 1) --L.th;   // un-tuned default: an even tile height (half a tile per CTA)
+  if (L.pair && (L.th % 2 || (L.tw * L.th) % 16)) L.pair = 0;
   if (L.xr && L.tw % 8) return fail(2, "tap-reuse tiles must be a multiple of 8 pixels wide");
   L.tiles_x = (L.Wo + L.tw - 1) / L.tw;
   L.tiles_y = (L.Ho + L.th - 1) / L.th;
