@@ -301,8 +301,9 @@ def test_predict_batch_api():
         det.predict_batch([images[0]] * 4)
 
 
-@pytest.mark.parametrize("swap,xr,cluster", [("1", "1", "1"), ("1", "1", "0"), ("1", "0", "1"), ("1", "0", "0"), ("0", "0", "0")])
-def test_kernel_variants_every_buffer_small(monkeypatch, swap, xr, cluster):
+@pytest.mark.parametrize("swap,xr,cluster,pair", [("1", "1", "1", "0"), ("1", "1", "0", "1"), ("1", "1", "0", "0"), ("1", "0", "1", "0"), ("1", "0", "0", "0"),
+                                                  ("0", "0", "0", "0")])
+def test_kernel_variants_every_buffer_small(monkeypatch, swap, xr, cluster, pair):
     """The un-tuned heuristic only uses the operand-swapped kernel (and its 3x3 tap-reuse variant) on large
     maps; force it onto every eligible layer of the small case - and switch the tap reuse off - so that each
     variant is checked buffer by buffer against the CPU interpretation of the plan."""
@@ -311,13 +312,15 @@ def test_kernel_variants_every_buffer_small(monkeypatch, swap, xr, cluster):
     monkeypatch.setenv("VGGHEADS_B200_SWAP", swap)
     monkeypatch.setenv("VGGHEADS_B200_XR", xr)
     monkeypatch.setenv("VGGHEADS_B200_CLUSTER", cluster)   # CTA pairs sharing the weight stream (odd tile counts: filler tiles)
+    monkeypatch.setenv("VGGHEADS_B200_PAIR", pair)         # cta_group::2 MMA pairs on the layers with >= 256 output channels
     S, B = 128, 3
     eng = Engine(no.synthetic_weights(4), B, S)
     used = [eng.op_config(i) for i, op in enumerate(eng.plan.ops) if op.kind == 1]
     if swap == "1":
         assert any(c["mt"] < 0 for c in used)
         assert any(c["stages"] >= 100 for c in used) == (xr == "1")   # op_config reports tap reuse as 100*pixel slots + weight slots
-        assert any(c["mt"] <= -11 for c in used) == (cluster == "1")  # ... and CTA pairs as mt = -(10 + k-blocks per stage)
+        assert any(-20 < c["mt"] <= -11 for c in used) == (cluster == "1")  # ... weight-multicast pairs as mt = -(10 + k-blocks per stage)
+        assert any(c["mt"] <= -21 for c in used) == (pair == "1")           # ... and cta_group::2 MMA pairs as mt = -(20 + ...)
     torch.manual_seed(1)
     img = torch.randint(0, 256, (B, S, S, 3), dtype=torch.uint8)
     eng.forward(img.cuda())
