@@ -40,14 +40,17 @@ for line in open(sys.argv[1]):
         gw = cout // G
         items = tiles * G
         xr = st >= 100
-        if xr:
+        pair = mt <= -20   # cta_group::2: each CTA of a pair stages half a pixel tile and supplies N/2 operand rows per MMA
+        if xr and pair:
+            ingest_item = cblks * (3 * (th // 2 + 2) * tw * bk * 2 + 9 * gw * bk * 2)
+        elif xr:
             ingest_item = cblks * (3 * (th + 2) * tw * bk * 2 + 9 * gw * bk * 2)
         else:
             ingest_item = taps * cblks * (npix * bk * 2 + gw * bk * 2)
         mma_item = taps * cblks * (bk // 16) * 2.0 * 128 * npix * 16
         n_mma = taps * cblks * (bk // 16)
-        smem_item = ingest_item + n_mma * (128 + npix) * 32 + 2 * npix * gw * es_out   # fills + MMA operand reads + staging write / store read
-        kind = "swap+XR" if xr else "swap"
+        smem_item = ingest_item + n_mma * (128 + (npix // 2 if pair else npix)) * 32 + 2 * npix * gw * es_out   # fills + MMA operand reads + staging write / store read
+        kind = "pair+XR" if pair else "swap+XR" if xr else "swap"
     else:       # pixels on M (mt tiles of 128), Cout tile on N
         n_tiles = math.ceil(cout / bn)
         items = math.ceil(B * Ho * Ho / (128 * mt)) * n_tiles
