@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -q -m gpu > gpurun_out/r2_final_gputests.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r2_final_gputests.log
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_final_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/r2_final_smoke.log
 timeout 600 python bench.py --impl reference --gpus 1 --steps 5 --warmup 2 > gpurun_out/r2_final_reference_arm.json 2> gpurun_out/r2_final_reference_arm.err; echo "reference arm rc=$?"
-/usr/bin/time -v timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r2_final_bench_1gpu.json 2> gpurun_out/r2_final_bench_1gpu.err; echo "bench rc=$?"; grep -E "Elapsed|Maximum resident" gpurun_out/r2_final_bench_1gpu.err
+SECONDS=0; timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r2_final_bench_1gpu.json 2> gpurun_out/r2_final_bench_1gpu.err; echo "bench rc=$?"; echo "bench wall ${SECONDS}s"
 python - <<'PY'
 import json
 d=json.loads(open("gpurun_out/r2_final_bench_1gpu.json").read().strip().splitlines()[-1])
