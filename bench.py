@@ -192,7 +192,11 @@ def _config(n, batch=PER_GPU_BATCH, dense_heads=False, gather=None):
                         "superset of configs[1]; configs[3] = the same with --per-gpu-batch 32 on 8 GPUs",
             "global_batch": batch * n, "image_size": IMAGE_SIZE, "heads_per_image": HEADS_PER_IMAGE,
             "parallelism": (f"dp{n} (batch-sharded; predictions gathered to rank 0 every step: {gather})" if n > 1 else "single GPU"),
-            "weights": "seeded random-init, deploy (re-parameterised) form", "in_flight": "2 batches per GPU (two detector handles on two streams; --engines)",
+            "weights": "seeded random-init, deploy (re-parameterised) form",
+            "precision": "activations and weights stored in the 16-bit format named by `dtype` (fp16 by default: 11 significant bits, the class of "
+                         "the TF32 convs the reference runs on a GPU; --act-dtype bf16 for the other), fp32 accumulation; parity.end_to_end "
+                         "holds the measured distance to the fp32 oracle for both formats and for the fp32-class parity mode",
+            "in_flight": "2 batches per GPU (two detector handles on two streams; --engines)",
             "l2": f"per-step working set ~{0.157 * batch:.0f} GB >> 126 MB L2; 4 rotating input batches"}
 
 
@@ -223,8 +227,9 @@ def parity_check(eng, boxes, scores, batch):
 
 def parity_end_to_end(weights, batch=2):
     """End-to-end precision of the conv path on `batch` images of the workload, with oracle/ as the checker: the fp32
-    oracle network (torch-CPU) against (a) the throughput mode (bf16 operands, bf16 activations) and (b) the parity mode
-    (three-term split bf16: fp32-class arithmetic on the same tensor-core kernels).  Per stage max-abs-error relative to
+    oracle network (torch-CPU) against (a) the throughput mode in the measured 16-bit storage format (`fast`; fp16 by
+    default) and in the other one (`fast_bf16` / `fast_fp16`) and (b) the parity mode (three-term split bf16: fp32-class
+    arithmetic on the same tensor-core kernels).  Per stage max-abs-error relative to
     the stage's max |value|; then, on REAL network outputs (threshold at the 99.5th score percentile, as random weights
     never reach 0.5): are the kept anchor ids those of `utils.nms` on the oracle's boxes / scores, and how far are the
     decoded vertices from the oracle's (bar of the metric: 1e-4 px)."""
@@ -244,8 +249,14 @@ def parity_end_to_end(weights, batch=2):
         want_ids = [nms_oracle.select_nms(ob[b].numpy(), os_[b, :, 0].numpy(), thr, IOU, TOPK, 100) for b in range(batch)]
         out = {"batch": batch, "conf_threshold": thr, "reference_heads": [int(len(k)) for k in want_ids],
                "checker": "oracle/net_oracle.DeployNet (torch-CPU fp32) + utils.nms / FLAME restatements on the same images"}
-        for mode in ("parity", "fast"):
-            eng = Engine(weights, batch, IMAGE_SIZE, sparse_heads=False, parity=(mode == "parity"))
+        from head_detector_b200 import arch
+
+        fast_dt = arch.default_act_dtype()                       # the format of the measured step
+        other_dt = "bf16" if fast_dt == "fp16" else "fp16"
+        out["fast_act_dtype"] = fast_dt
+        for mode in ("parity", "fast", "fast_" + other_dt):
+            eng = Engine(weights, batch, IMAGE_SIZE, sparse_heads=False, parity=(mode == "parity"),
+                         act_dtype=None if mode == "parity" else (fast_dt if mode == "fast" else other_dt))
             boxes, scores = eng.forward(img.cuda())
             eng.postprocess(thr, IOU, TOPK)
             torch.cuda.synchronize()
@@ -526,7 +537,7 @@ def run_ours(args, rank, world, local_rank):
         line = {
             "metric": "images/sec (640x640)", "value": imgs / (ms_dev * 1e-3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": _config(world, B, args.dense_heads, pipe.gather),
+            "vs_baseline": None, "dtype": eng.act_dtype, "data": "synthetic", "config": _config(world, B, args.dense_heads, pipe.gather),
             "clocks": clocks,
             "e2e": {"value": imgs / e2e_s, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "mode": "vgh_detector_submit_host/collect_host over 2 detector handles (3 batches in flight)" + (" + gather of every step's record to rank 0" if world > 1 else "")},
@@ -643,6 +654,8 @@ def main():
     ap.add_argument("--dense-heads", action="store_true",
                     help="run the FLAME branch of the heads on the whole feature maps (as the reference graph does) instead of on the "
                          "8x8 windows around the NMS survivors; same predictions, ~20 %% more work")
+    ap.add_argument("--act-dtype", default=None, choices=["fp16", "bf16"],
+                    help="16-bit storage format of activations and weights (default: $VGGHEADS_B200_ACT or fp16; fp32 accumulation either way)")
     ap.add_argument("--engines", type=int, default=2, help="detector handles per GPU = batches in flight on the device-timed path")
     ap.add_argument("--no-autotune", action="store_true", help="skip the per-layer configuration search (tests)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg of the N=1 line (tests)")
@@ -655,6 +668,8 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank)
         return
+    if args.act_dtype:
+        os.environ["VGGHEADS_B200_ACT"] = args.act_dtype   # every Engine of this process (extras included) follows
     import torch
 
     if not torch.cuda.is_available():

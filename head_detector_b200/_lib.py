@@ -41,7 +41,7 @@ class NetDesc(C.Structure):
         ("weights_host", C.c_void_p), ("n_weights", C.c_int64),
         ("bias_host", C.c_void_p), ("n_bias", C.c_int64),
         ("reg_buf", C.c_int32 * 3), ("flame_buf", C.c_int32 * 3),
-        ("keep_k", C.c_int32), ("n_dense_ops", C.c_int32), ("split", C.c_int32),
+        ("keep_k", C.c_int32), ("n_dense_ops", C.c_int32), ("split", C.c_int32), ("act_f16", C.c_int32),
     ]
 
 

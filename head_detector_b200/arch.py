@@ -87,6 +87,7 @@ class Plan:
         self.n_dense_ops: Optional[int] = None  # sparse heads: ops [0, n_dense_ops) run before select/NMS, the rest after
         self.patch_cap = 0  # sparse heads: patch capacity per level (batch * keep_top_k)
         self.split = False  # parity mode (split_plan): bf16 buffers hold six planes [h|m|h|m|h|l] per 32-channel granule
+        self.act_dtype = "bf16"  # storage format of the 16-bit activation buffers and of the packed weights (ACT_DTYPES)
 
     # -- helpers
     def buf(self, name, res, C, fp32=0):
@@ -139,11 +140,31 @@ class Plan:
             self.simple(name + ".conv3", (cat, 0, 2 * hid), dst, cout)
 
 
-def build_plan(image_size: int = 640, sparse_heads: Optional[Tuple[int, int]] = None, fused_stem: bool = True) -> Plan:
+# 16-bit storage formats of the throughput mode.  fp16 (default): 11 significant bits - the precision class of the TF32
+# convolutions the reference's own GPU path runs by default, and the format the released model was trained in (AMP:
+# yolo_head_training/configs/yolo_heads_l.yaml:21 `mixed_precision: True`), so its activations are known to fit the
+# range.  bf16: 8 significant bits, fp32's range.  Same kernels and tensor-core rate either way.
+ACT_DTYPES = {"bf16": torch.bfloat16, "fp16": torch.float16}
+
+
+def default_act_dtype() -> str:
+    import os
+
+    v = os.environ.get("VGGHEADS_B200_ACT", "fp16").lower()
+    if v not in ACT_DTYPES:
+        raise ValueError(f"VGGHEADS_B200_ACT must be one of {sorted(ACT_DTYPES)}, got {v!r}")
+    return v
+
+
+def build_plan(image_size: int = 640, sparse_heads: Optional[Tuple[int, int]] = None, fused_stem: bool = True,
+               act_dtype: str = "bf16") -> Plan:
     """`sparse_heads=(batch, keep_top_k)` builds the two-phase plan: the dense ops end with the box branch; the FLAME
     branch of every level follows select/NMS and runs on survivor patches (see PATCH).  `fused_stem=False` keeps the
-    two-op stem (uint8 im2col buffer + Cin = 32 1x1 conv on the tensor-core GEMM kernel) that the parity mode splits."""
+    two-op stem (uint8 im2col buffer + Cin = 32 1x1 conv on the tensor-core GEMM kernel) that the parity mode splits.
+    `act_dtype`: "bf16" | "fp16" (ACT_DTYPES)."""
+    assert act_dtype in ACT_DTYPES, act_dtype
     P = Plan(image_size)
+    P.act_dtype = act_dtype
     if sparse_heads is not None:
         P.patch_cap = int(sparse_heads[0]) * int(sparse_heads[1])
     S = image_size
@@ -290,6 +311,7 @@ def split_plan(P: Plan) -> Plan:
     every op are scaled by 6; fp32 buffers (raw head outputs) are untouched.  Pure bookkeeping - the arithmetic change
     is in the epilogue (three-term split store) and in `pack` (weight terms along K)."""
     assert P.n_dense_ops is None, "parity mode runs the dense-heads plan"
+    assert P.act_dtype == "bf16", "parity mode splits values into bf16 terms"
     P.split = True
     is_bf16 = [not fp32 for (_, _, _, fp32) in P.bufs]
     P.bufs = [(h, w, c * SPLIT_PLANES if not fp32 else c, fp32) for (h, w, c, fp32) in P.bufs]
@@ -329,7 +351,7 @@ def _auto_block_n(cout: int, up: int, up_cout: int) -> int:
 @dataclass
 class PackedNet:
     plan: Plan
-    weights: np.ndarray   # uint16 bf16 bits
+    weights: np.ndarray   # uint16: bf16 or fp16 bits (plan.act_dtype)
     bias: np.ndarray      # float32
     op_meta: List[dict]
 
@@ -377,7 +399,10 @@ def pack(plan: Plan, w: Dict[str, torch.Tensor]) -> PackedNet:
             G = M.reshape(n_pad, taps, cin // 32, 1, 32)
             M = torch.cat([terms[t].reshape_as(G) for t in SPLIT_WEIGHT_TERM], dim=3).reshape(n_pad, taps, cin * SPLIT_PLANES)
             cin = cin * SPLIT_PLANES
-        chunk = M.reshape(-1).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+        q = M.reshape(-1).to(ACT_DTYPES[plan.act_dtype])
+        if not bool(torch.isfinite(q).all()):
+            raise ValueError(f"{op.label}: weights do not fit {plan.act_dtype}; use act_dtype='bf16'")
+        chunk = q.view(torch.int16).numpy().view(np.uint16)
         pad = (-chunk.size) % 64  # keep every TMA base address 128-byte aligned
         if pad:
             chunk = np.concatenate([chunk, np.zeros(pad, dtype=np.uint16)])

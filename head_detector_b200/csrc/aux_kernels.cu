@@ -2,6 +2,7 @@
 // max-pools, DFL/sigmoid box decode, FLAME-row assembly (dense or for NMS survivors only).
 // All HBM-bound elementwise/stencil work: coalesced 16-byte accesses, no reshaping into GEMMs.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -70,16 +71,24 @@ int stem_pack_launch(const uint8_t* img, __nv_bfloat16* out, int B, int S, int s
 // ---------------------------------------------------------------------------------------- SPP
 // max-pool k=5,9,13 stride 1 (pad k/2 with -inf) of channel slice [0,C) of a [B,H,W,4C] buffer into
 // slices 1,2,3.
+template <bool F16>
 __device__ __forceinline__ void max8(uint4& m, const uint4 v) {
-  __nv_bfloat162* a = reinterpret_cast<__nv_bfloat162*>(&m);
-  const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&v);
+  if constexpr (F16) {
+    __half2* a = reinterpret_cast<__half2*>(&m);
+    const __half2* b = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) a[i] = __hmax2(a[i], b[i]);
+    for (int i = 0; i < 4; ++i) a[i] = __hmax2(a[i], b[i]);
+  } else {
+    __nv_bfloat162* a = reinterpret_cast<__nv_bfloat162*>(&m);
+    const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = __hmax2(a[i], b[i]);
+  }
 }
 
 // CTA = one image x CH channels; the H x W x CH slab lives in shared memory and the three pools are
 // computed as cascaded separable 5-wide maxima (mp9 = mp5(mp5), mp13 = mp5(mp9); -inf padding).
-template <bool kRows>
+template <bool kRows, bool F16>
 __device__ __forceinline__ void max5_pass(const uint4* __restrict__ src, uint4* __restrict__ dst, int H, int W, int L) {
   for (int i = threadIdx.x; i < H * W * L; i += blockDim.x) {
     const int l = i % L, pix = i / L;
@@ -90,12 +99,13 @@ __device__ __forceinline__ void max5_pass(const uint4* __restrict__ src, uint4* 
       if (d == 0) continue;
       const int xx = kRows ? x + d : x, yy = kRows ? y : y + d;
       if (xx < 0 || xx >= W || yy < 0 || yy >= H) continue;
-      max8(m, src[(yy * W + xx) * L + l]);
+      max8<F16>(m, src[(yy * W + xx) * L + l]);
     }
     dst[i] = m;
   }
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(256) spp_pool_kernel(__nv_bfloat16* __restrict__ buf, int B, int H, int W, int C, int CH) {
   extern __shared__ __align__(16) uint8_t spp_smem[];
   const int L = CH / 8;  // uint4 lanes per pixel
@@ -112,9 +122,9 @@ __global__ void __launch_bounds__(256) spp_pool_kernel(__nv_bfloat16* __restrict
   uint4* cur = b0;
   uint4* out = b2;
   for (int k = 1; k <= 3; ++k) {
-    max5_pass<true>(cur, b1, H, W, L);
+    max5_pass<true, F16>(cur, b1, H, W, L);
     __syncthreads();
-    max5_pass<false>(b1, out, H, W, L);
+    max5_pass<false, F16>(b1, out, H, W, L);
     __syncthreads();
     for (int i = threadIdx.x; i < H * W * L; i += blockDim.x)
       *reinterpret_cast<uint4*>(base + static_cast<size_t>(i / L) * CT + k * C + (i % L) * 8) = out[i];
@@ -124,14 +134,19 @@ __global__ void __launch_bounds__(256) spp_pool_kernel(__nv_bfloat16* __restrict
   }
 }
 
-int spp_pool_launch(__nv_bfloat16* buf, int B, int H, int W, int C, cudaStream_t stream) {
+int spp_pool_launch(__nv_bfloat16* buf, int B, int H, int W, int C, int f16, cudaStream_t stream) {
   int CH = 32;
   while (CH > 8 && static_cast<size_t>(H) * W * CH * 2 * 3 > 160 * 1024) CH >>= 1;
   if (C % CH) return 1;
   const size_t smem = static_cast<size_t>(H) * W * CH * 2 * 3;
-  static SmemOptIn opt_in;
-  if (ensure_dynamic_smem(spp_pool_kernel, opt_in, smem) != cudaSuccess) return 1;
-  spp_pool_kernel<<<B * (C / CH), 256, smem, stream>>>(buf, B, H, W, C, CH);
+  static SmemOptIn opt_in[2];
+  if (f16) {
+    if (ensure_dynamic_smem(spp_pool_kernel<true>, opt_in[1], smem) != cudaSuccess) return 1;
+    spp_pool_kernel<true><<<B * (C / CH), 256, smem, stream>>>(buf, B, H, W, C, CH);
+  } else {
+    if (ensure_dynamic_smem(spp_pool_kernel<false>, opt_in[0], smem) != cudaSuccess) return 1;
+    spp_pool_kernel<false><<<B * (C / CH), 256, smem, stream>>>(buf, B, H, W, C, CH);
+  }
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

@@ -26,9 +26,10 @@ constexpr int kPatch = 8, kPatchC = 3;  // survivor patch size / offset of the a
 // split != 0 (parity mode): the 32-wide row goes to planes 0, 2, 4 of a 192-wide granule (uint8 values are exact in bf16: m = l = 0)
 int stem_pack_launch(const uint8_t* img, __nv_bfloat16* out, int B, int S, int split, cudaStream_t stream);
 // fused stem (stem_conv.cu): uint8 image -> conv3x3 s2 (3 -> 48, K-major weights [>=48][32]) + bias + ReLU -> bf16 [B,S/2,S/2,out_cstride]
+// f16 != 0: weights and output are IEEE fp16 instead of bf16 (same pointer types)
 int stem_conv_launch(const uint8_t* img, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* out, int B, int S, int out_cstride,
-                     int relu, cudaStream_t stream);
-int spp_pool_launch(__nv_bfloat16* buf, int B, int H, int W, int C, cudaStream_t stream);
+                     int relu, int f16, cudaStream_t stream);
+int spp_pool_launch(__nv_bfloat16* buf, int B, int H, int W, int C, int f16, cudaStream_t stream);
 // parity mode: the same pools on split activations (C logical channels = 6C physical per slice): max over y = h + m + l
 int spp_pool_split_launch(__nv_bfloat16* buf, int B, int H, int W, int C, cudaStream_t stream);
 int box_decode_launch(const DecodeLevels& lv, float* boxes, float* scores, int B, int A, cudaStream_t stream);

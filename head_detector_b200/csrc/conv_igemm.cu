@@ -16,6 +16,26 @@ constexpr int kBlockM = 128;
 constexpr int kEpiWarps = 8;                   // 2 per TMEM lane quarter, each takes every other 16-column chunk
 constexpr int kThreads = 64 + 32 * kEpiWarps;  // warp0 TMA, warp1 MMA/TMEM, warps 2..9 epilogue
 
+// epilogue helpers: 16 channels of one pixel, activations stored as bf16 or fp16 (ConvLaunch::f16)
+template <bool F16>
+__device__ __forceinline__ void add_residual16(float (&f)[16], const uint4 (&rq)[2], float alpha) {
+  const uint32_t w[8] = {rq[0].x, rq[0].y, rq[0].z, rq[0].w, rq[1].x, rq[1].y, rq[1].z, rq[1].w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 r = unpack16x2<F16>(w[i]);
+    f[2 * i] = fmaf(alpha, r.x, f[2 * i]);
+    f[2 * i + 1] = fmaf(alpha, r.y, f[2 * i + 1]);
+  }
+}
+template <bool F16>
+__device__ __forceinline__ void store_row16(const float (&f)[16], uint4* op) {
+  uint32_t w[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) w[i] = pack16x2<F16>(f[2 * i], f[2 * i + 1]);
+  op[0] = make_uint4(w[0], w[1], w[2], w[3]);
+  op[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
 // Persistent, warp-specialised implicit-GEMM conv.  Each CTA (one per SM) walks work items
 // item = blockIdx.x + i*gridDim.x, item -> (M group of `mt` 128-pixel tiles, N tile).  The shared-memory
 // ring (TMA -> MMA) runs continuously across items; accumulators are double-buffered in TMEM when
@@ -138,7 +158,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   } else if (warp == 1) {
     if (lane == 0) {
       // ===================== MMA issuer (one thread) =====================
-      const uint32_t idesc = umma_idesc_bf16(kBlockM, static_cast<uint32_t>(p.block_n));
+      const uint32_t idesc = umma_idesc_16(kBlockM, static_cast<uint32_t>(p.block_n), p.f16 != 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -305,28 +325,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
               continue;
             }
             if (p.res != nullptr) {
-              const uint32_t w[8] = {rq[g][0].x, rq[g][0].y, rq[g][0].z, rq[g][0].w, rq[g][1].x, rq[g][1].y, rq[g][1].z, rq[g][1].w};
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
-                f[2 * i] = fmaf(p.res_alpha, __bfloat162float(h.x), f[2 * i]);
-                f[2 * i + 1] = fmaf(p.res_alpha, __bfloat162float(h.y), f[2 * i + 1]);
-              }
+              if (p.f16) add_residual16<true>(f, rq[g], p.res_alpha);
+              else add_residual16<false>(f, rq[g], p.res_alpha);
             }
             if (p.out_fp32) {
               float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + out_off + c * 16);
 #pragma unroll
               for (int i = 0; i < 4; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
             } else {
-              uint32_t w[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-                w[i] = *reinterpret_cast<uint32_t*>(&h);
-              }
               uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + out_off + c * 16);
-              op[0] = make_uint4(w[0], w[1], w[2], w[3]);
-              op[1] = make_uint4(w[4], w[5], w[6], w[7]);
+              if (p.f16) store_row16<true>(f, op);
+              else store_row16<false>(f, op);
             }
           }
         }

@@ -50,6 +50,7 @@ struct ConvLaunch {
   int pair;                      // swapped tap-reuse kernel: 1 = CTA pairs run one cta_group::2 MMA (M = 256 = two channel groups) per pixel tile
   int acc_stages, n_tiles, num_items;  // TMEM accumulator stages (1|2), N tiles, work items (persistent CTAs)
   int split;                     // normal kernel, parity mode: store y as bf16 terms h|m|l in six planes per 32-channel granule
+  int f16;                       // 16-bit activations and weights are IEEE fp16 instead of bf16 (MMA operand format + epilogue conversions)
 };
 
 // Host side (conv_igemm.cu)

@@ -60,6 +60,20 @@ namespace vgh {
 constexpr int kSwapEpiWarps = 8;
 constexpr int kSwapThreads = 64 + 32 * kSwapEpiWarps;
 
+// epilogue: 16 pixels of one channel (one TMEM lane) -> + bias, ReLU, + alpha * residual (already in the staging tile) ->
+// 16-bit activation (bf16 or fp16, ConvLaunch::f16) into the [pixel][channel] staging tile
+template <bool F16>
+__device__ __forceinline__ void stage_column16(const uint32_t (&v)[16], unsigned short* sp, int gw, float bias, bool relu, bool has_res,
+                                               float alpha) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float x = __uint_as_float(v[j]) + bias;
+    if (relu) x = fmaxf(x, 0.f);
+    if (has_res) x = fmaf(alpha, unpack16<F16>(sp[j * gw]), x);
+    sp[j * gw] = pack16<F16>(x);
+  }
+}
+
 template <int BK, bool XR, bool PAIR = false>
 __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const __grid_constant__ ConvLaunch p) {
   static_assert(!PAIR || XR, "CTA pairs are built for the tap-reuse variant");
@@ -265,7 +279,7 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
   } else if (warp == 1) {
     if (lane == 0 && leader) {
       // ===================== MMA issuer (PAIR: the leader CTA, for both) =====================
-      const uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, static_cast<uint32_t>(npix));
+      const uint32_t idesc = umma_idesc_16(PAIR ? 256 : 128, static_cast<uint32_t>(npix), p.f16 != 0);
       int stage = 0, xs = 0;
       uint32_t phase = 0, xphase = 0;
       int acc = 0;
@@ -390,13 +404,8 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
             }
           } else {
             unsigned short* sp = reinterpret_cast<unsigned short*>(stile) + (c * 16) * gw + ch;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float x = __uint_as_float(v[j]) + bias;
-              if (p.relu) x = fmaxf(x, 0.f);
-              if (has_res) x = fmaf(p.res_alpha, __uint_as_float(static_cast<uint32_t>(sp[j * gw]) << 16), x);
-              sp[j * gw] = __bfloat16_as_ushort(__float2bfloat16_rn(x));
-            }
+            if (p.f16) stage_column16<true>(v, sp, gw, bias, p.relu != 0, has_res, p.res_alpha);
+            else stage_column16<false>(v, sp, gw, bias, p.relu != 0, has_res, p.res_alpha);
           }
         }
       }

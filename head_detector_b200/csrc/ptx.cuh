@@ -4,6 +4,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 namespace vgh {
@@ -236,9 +238,41 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t row_
   d |= layout << 61;
   return d;
 }
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, MxN tile.
-__host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+// kind::f16 instruction descriptor: D=f32, A=B=bf16 (format 1) or fp16 (format 0), both K-major, MxN tile.
+__host__ __device__ __forceinline__ uint32_t umma_idesc_16(uint32_t M, uint32_t N, bool f16) {
+  const uint32_t fmt = f16 ? 0u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// 16-bit activation storage: bf16 (default of the parity / split mode and of act_dtype = bf16) or IEEE fp16
+// (act_dtype = fp16: 11 significant bits instead of 8 at the same tensor-core rate).
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16x2(float a, float b) {
+  if constexpr (F16) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  } else {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
+}
+template <bool F16>
+__device__ __forceinline__ float2 unpack16x2(uint32_t w) {
+  if constexpr (F16) {
+    return __half22float2(*reinterpret_cast<const __half2*>(&w));
+  } else {
+    return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
+  }
+}
+template <bool F16>
+__device__ __forceinline__ unsigned short pack16(float a) {
+  if constexpr (F16) return __half_as_ushort(__float2half_rn(a));
+  else return __bfloat16_as_ushort(__float2bfloat16_rn(a));
+}
+template <bool F16>
+__device__ __forceinline__ float unpack16(unsigned short u) {
+  if constexpr (F16) return __half2float(__ushort_as_half(u));
+  else return __uint_as_float(static_cast<uint32_t>(u) << 16);
 }
 
 }  // namespace vgh

@@ -10,6 +10,7 @@
 // mma.sync.m16n8k16 (K = 27 padded to 32, N = 48): 20 GFLOP per 64 images - a tcgen05 / TMEM pipeline would buy
 // nothing for a kernel that waits on its 128-byte output rows, which leave through a padded staging tile as full lines.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -26,21 +27,44 @@ constexpr int kStemOutPitch = 72;             // staging row pitch in bf16 (64 +
 constexpr int kStemWPitch = 40;               // weight row pitch in bf16 (32 + 8: conflict-free fragment reads)
 constexpr int kStemFetch = (kStemIn + 7) / 8; // window rows per warp (8 warps)
 
-__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+template <bool F16>
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if constexpr (F16)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// two adjacent uint8 (low 16 bits of v) -> packed bf16x2, exact: 0x4B000000 | b is the float 2^23 + b
-__device__ __forceinline__ uint32_t u8x2_to_bf16x2(uint32_t v) {
-  const float f0 = __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7540)) - 8388608.f;
-  const float f1 = __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7541)) - 8388608.f;
-  const __nv_bfloat162 p = __floats2bfloat162_rn(f0, f1);
-  return *reinterpret_cast<const uint32_t*>(&p);
+// two adjacent uint8 (low 16 bits of v) -> packed 16-bit floats, exact.  bf16: 0x4B000000 | b is the float 2^23 + b;
+// fp16: 0x6400 | b is the half 1024 + b.
+template <bool F16>
+__device__ __forceinline__ uint32_t u8x2_to_16x2(uint32_t v) {
+  if constexpr (F16) {
+    const uint32_t biased = __byte_perm(v, 0x64u, 0x4140);   // bytes [b0, 0x64, b1, 0x64]
+    const uint32_t k1024 = 0x64006400u;
+    const __half2 h = __hsub2(*reinterpret_cast<const __half2*>(&biased), *reinterpret_cast<const __half2*>(&k1024));
+    return *reinterpret_cast<const uint32_t*>(&h);
+  } else {
+    const float f0 = __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7540)) - 8388608.f;
+    const float f1 = __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7541)) - 8388608.f;
+    const __nv_bfloat162 p = __floats2bfloat162_rn(f0, f1);
+    return *reinterpret_cast<const uint32_t*>(&p);
+  }
+}
+__device__ __forceinline__ uint32_t pack_f2(float a, float b, bool f16) {   // keep in step with ptx.cuh pack16x2 (not included here)
+  if (f16) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-// w: packed K-major weights [>= 48][32] bf16 (27 taps in (ky,kx,c) order + 5 zeros), bias [48] fp32.
+// w: packed K-major weights [>= 48][32] bf16 / fp16 (F16; the pointer types say bf16 for both) (27 taps in (ky,kx,c) order + 5 zeros), bias [48] fp32.
 // Persistent CTAs walk the (image, tile) list; the input window of tile i+1 is fetched into registers while tile i is
 // being multiplied.  The kernel is instruction-issue bound if written naively (profiles/r2_ncu_full_stem_v1.txt: 9400
 // warp instructions per tile, 67 % issue-active), so:
@@ -49,6 +73,7 @@ __device__ __forceinline__ uint32_t u8x2_to_bf16x2(uint32_t v) {
 //   * inside the kernel the 27 taps are ordered k' = ky*10 + (kx*3 + c) (weights permuted when they are staged), so that
 //     every A-fragment register is two ADJACENT, 2-byte aligned window bytes: one LDS.U16 + 2 PRMT + 2 FADD + 1 pack;
 //   * the copy-out walks rows with a constant address increment.
+template <bool F16>
 __global__ void __launch_bounds__(256, 4) stem_conv_kernel(const uint8_t* __restrict__ img, const __nv_bfloat16* __restrict__ w,
                                                            const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int S, int B,
                                                            int out_cstride, int relu) {
@@ -130,23 +155,22 @@ __global__ void __launch_bounds__(256, 4) stem_conv_kernel(const uint8_t* __rest
         for (int h = 0; h < 2; ++h) {
           // a0a1 (row g, k 2t..), a2a3 (row g+8, k 2t..), a4a5 (row g, k 2t+8..), a6a7 (row g+8, k 2t+8..)
           const int o = koff[s][h];
-          a[s][2 * h] = o >= 0 ? u8x2_to_bf16x2(*reinterpret_cast<const uint16_t*>(r0 + o)) : 0u;
-          a[s][2 * h + 1] = o >= 0 ? u8x2_to_bf16x2(*reinterpret_cast<const uint16_t*>(r0 + 48 + o)) : 0u;
+          a[s][2 * h] = o >= 0 ? u8x2_to_16x2<F16>(*reinterpret_cast<const uint16_t*>(r0 + o)) : 0u;
+          a[s][2 * h + 1] = o >= 0 ? u8x2_to_16x2<F16>(*reinterpret_cast<const uint16_t*>(r0 + 48 + o)) : 0u;
         }
 #pragma unroll
       for (int j = 0; j < 6; ++j) {
         const float2 bj = *reinterpret_cast<const float2*>(&bsm[8 * j + 2 * t4]);
         float d[4] = {bj.x, bj.y, bj.x, bj.y};
         const uint32_t* wr = wsm + (8 * j + g) * (kStemWPitch / 2) + t4;   // row n = 8j + g: k' = 2t, 2t+8 (+16 for the second step)
-        mma_bf16_16816(d, a[0], wr[0], wr[4]);
-        mma_bf16_16816(d, a[1], wr[8], wr[12]);
+        mma_16816<F16>(d, a[0], wr[0], wr[4]);
+        mma_16816<F16>(d, a[1], wr[8], wr[12]);
         if (relu) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) d[i] = fmaxf(d[i], 0.f);
         }
-        __nv_bfloat162 lo = __floats2bfloat162_rn(d[0], d[1]), hi = __floats2bfloat162_rn(d[2], d[3]);
-        *reinterpret_cast<__nv_bfloat162*>(&stage[(oy * kStemTile + g) * kStemOutPitch + 8 * j + 2 * t4]) = lo;
-        *reinterpret_cast<__nv_bfloat162*>(&stage[(oy * kStemTile + g + 8) * kStemOutPitch + 8 * j + 2 * t4]) = hi;
+        *reinterpret_cast<uint32_t*>(&stage[(oy * kStemTile + g) * kStemOutPitch + 8 * j + 2 * t4]) = pack_f2(d[0], d[1], F16);
+        *reinterpret_cast<uint32_t*>(&stage[(oy * kStemTile + g + 8) * kStemOutPitch + 8 * j + 2 * t4]) = pack_f2(d[2], d[3], F16);
       }
     }
     __syncthreads();
@@ -166,17 +190,20 @@ __global__ void __launch_bounds__(256, 4) stem_conv_kernel(const uint8_t* __rest
 }
 
 int stem_conv_launch(const uint8_t* img, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* out, int B, int S, int out_cstride,
-                     int relu, cudaStream_t stream) {
+                     int relu, int f16, cudaStream_t stream) {
   const int Ho = S / 2;
   if (Ho % kStemTile || out_cstride < 64 || out_cstride % 8 || (reinterpret_cast<uintptr_t>(img) & 3)) return 1;
   static std::atomic<int> carveout_set[kMaxDevices];
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev >= 0 && dev < kMaxDevices && !carveout_set[dev].exchange(1))   // 4 CTAs x 44 KB static shared memory per SM
-    cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (dev >= 0 && dev < kMaxDevices && !carveout_set[dev].exchange(1)) {   // 4 CTAs x 44 KB static shared memory per SM
+    cudaFuncSetAttribute(stem_conv_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(stem_conv_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  }
   const int n_tiles = (Ho / kStemTile) * (Ho / kStemTile) * B;
   const int grid = n_tiles < 4 * device_sm_count() ? n_tiles : 4 * device_sm_count();
-  stem_conv_kernel<<<grid, 256, 0, stream>>>(img, w, bias, out, S, B, out_cstride, relu);
+  if (f16) stem_conv_kernel<true><<<grid, 256, 0, stream>>>(img, w, bias, out, S, B, out_cstride, relu);
+  else stem_conv_kernel<false><<<grid, 256, 0, stream>>>(img, w, bias, out, S, B, out_cstride, relu);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

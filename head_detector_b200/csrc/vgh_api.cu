@@ -140,6 +140,7 @@ struct vgh_detector {
   int n_dense_ops = 0, patch_cap = 0;
   bool sparse = false;
   bool split = false;  // parity mode: activations as split bf16 terms, normal (pixels-on-M) conv kernel only
+  bool f16 = false;    // 16-bit activations / weights are IEEE fp16 (vgh_net_desc.act_f16) instead of bf16
   int *head_level = nullptr, *head_patch = nullptr, *patch_src = nullptr, *level_rows = nullptr;
   cudaGraphExec_t graph = nullptr;
   cudaStream_t cap_stream = nullptr;  // capture needs a non-legacy stream; the graph then replays anywhere
@@ -269,6 +270,12 @@ static int pair_default() {
   const char* e = getenv("VGGHEADS_B200_PAIR");
   return (e && e[0] == '0') ? 0 : 1;
 }
+// deeper TMA rings for the 32-channel K blocks of the tap-reuse kernel (up to 16 weight stages, a fourth pixel slot as an
+// autotune candidate): VGGHEADS_B200_DEEP_RINGS = 0 restores the 8-stage cap (A/B aid)
+static bool deep_rings() {
+  const char* e = getenv("VGGHEADS_B200_DEEP_RINGS");
+  return !(e && e[0] == '0');
+}
 // test aid: VGGHEADS_B200_SWAP=1 makes the un-tuned heuristic pick the swapped kernel for every eligible op
 // (by default only large maps with Cout <= 128 do), so that small parity cases exercise it everywhere
 static bool swap_forced() {
@@ -360,6 +367,7 @@ static int build_conv(vgh_detector* d, OpRt& o) {
   L.relu = q.relu;
   L.out_fp32 = ob.fp32;
   L.split = (d->split && !ob.fp32) ? 1 : 0;
+  L.f16 = d->f16 ? 1 : 0;
   if (L.split && (q.cout % 32 || q.out_coff % 192 || (q.up && q.up_cout % 32))) return fail(2, "parity mode: channel slices must be whole 32-channel granules");
   if (q.up) {
     if (ob.H != 2 * ib.H || ob.W != 2 * ib.W) return fail(2, "transpose conv output buffer must be 2x the input");
@@ -391,7 +399,10 @@ static int build_conv(vgh_detector* d, OpRt& o) {
     int ws = (budget - xs * x_slot) / w_bytes;
     if (ws < 3) return fail(2, "tap-reuse variant does not fit shared memory (tile %dx%d, bk %d)", L.tw, L.th, o.bk);
     L.xslots = xs;
-    L.stages = ws > 8 ? 8 : ws;
+    // 32-channel K blocks (96-channel layers) have 8 KB weight stages: 8 of them leave half of the shared memory - i.e. of
+    // the bytes in flight that hide the L2 latency - unused, so the ring may go 16 deep
+    const int ring_cap = deep_rings() ? 16 : 8;
+    L.stages = ws > ring_cap ? ring_cap : ws;
   } else if (L.swap) {
     const int stage_bytes = 128 * o.bk * 2 + ((L.tw * L.th * o.bk * 2 + 1023) & ~1023);
     const int staging = (L.tw * L.th * L.gw * (ob.fp32 ? 4 : 2) + 1023) & ~1023;  // epilogue tile [pixels][channels]
@@ -469,7 +480,9 @@ extern "C" int vgh_detector_create(const vgh_net_desc* n, const vgh_flame* flame
   d->n_dense_ops = (n->n_dense_ops > 0 && n->n_dense_ops < n->n_ops) ? n->n_dense_ops : n->n_ops;
   d->sparse = d->n_dense_ops < n->n_ops;
   d->split = n->split != 0;
+  d->f16 = n->act_f16 != 0;
   if (d->split && d->sparse) return bail(fail(2, "parity (split) mode needs the dense-heads plan"));
+  if (d->split && d->f16) return bail(fail(2, "parity (split) mode stores bf16 terms: act_f16 must be 0"));
   // survivor patches are addressed as image << 20 | y << 10 | x (aux_kernels.cu: patch_src)
   if (d->sparse && (d->B > 4096 || d->S / 8 > 1024)) return bail(fail(1, "sparse heads: batch <= 4096 and image size <= 8192"));
   d->patch_cap = d->B * d->keep_k;
@@ -545,6 +558,7 @@ static int launch_op(vgh_detector* d, OpRt& o, const uint8_t* images, cudaStream
   int rc = 0;
   switch (o.d.kind) {
     case VGH_OP_STEM:
+      if (d->f16) return fail(2, "the two-op (im2col) stem writes bf16; fp16 activations use the fused stem (VGH_OP_STEM_CONV)");
       rc = stem_pack_launch(images, static_cast<__nv_bfloat16*>(d->buf_ptr[o.d.out_buf]), d->B, d->S, d->split ? 1 : 0, s);
       if (rc) return fail(5, "stem launch failed: %s", cudaGetErrorString(cudaGetLastError()));
       break;
@@ -553,7 +567,7 @@ static int launch_op(vgh_detector* d, OpRt& o, const uint8_t* images, cudaStream
       if (ob.fp32 || ob.H != d->S / 2 || o.d.k_total != 32 || o.d.cout != 64 || o.d.out_coff != 0)
         return fail(2, "fused stem: expects a bf16 [S/2,S/2,>=64] output at channel 0 and 32-wide packed taps");
       rc = stem_conv_launch(images, d->weights + o.d.w_off, d->bias + o.d.b_off, static_cast<__nv_bfloat16*>(d->buf_ptr[o.d.out_buf]), d->B, d->S,
-                            ob.C, o.d.relu, s);
+                            ob.C, o.d.relu, d->f16 ? 1 : 0, s);
       if (rc) return fail(5, "fused stem launch failed: %s", cudaGetErrorString(cudaGetLastError()));
       break;
     }
@@ -564,7 +578,7 @@ static int launch_op(vgh_detector* d, OpRt& o, const uint8_t* images, cudaStream
     case VGH_OP_SPP: {
       const vgh_buf_desc& b = d->bufs[o.d.in_buf];
       rc = d->split ? spp_pool_split_launch(static_cast<__nv_bfloat16*>(d->buf_ptr[o.d.in_buf]), d->B, b.H, b.W, o.d.cin, s)
-                    : spp_pool_launch(static_cast<__nv_bfloat16*>(d->buf_ptr[o.d.in_buf]), d->B, b.H, b.W, o.d.cin, s);
+                    : spp_pool_launch(static_cast<__nv_bfloat16*>(d->buf_ptr[o.d.in_buf]), d->B, b.H, b.W, o.d.cin, d->f16 ? 1 : 0, s);
       if (rc) return fail(5, "spp launch failed");
       break;
     }
@@ -764,7 +778,8 @@ extern "C" int vgh_detector_autotune(vgh_detector* d, int iters, void* stream) {
       }
       for (int ci = 0; ci < n_cand; ++ci) {
         const int ptw = cands[ci].tw, pth = cands[ci].th;
-        for (int xs : {2, 3}) for (int cl = 0; cl <= cluster_default(); ++cl) for (int pr = 0; pr <= pair_default(); ++pr) {
+        for (int xs : {2, 3, 4}) for (int cl = 0; cl <= cluster_default(); ++cl) for (int pr = 0; pr <= pair_default(); ++pr) {
+          if (xs == 4 && (o.bk != 32 || !deep_rings())) continue;   // a fourth pixel slot only fits next to the small 32-channel K blocks
           OpRt t = o;
           t.cfg_ks = 1; t.cfg_swap = 1; t.cfg_mt = 0; t.cfg_stages = 0; t.cfg_xr = 1; t.cfg_xslots = xs; t.cfg_cluster = cl; t.cfg_pair = pr;
           t.cfg_tw = ptw; t.cfg_th = pth;

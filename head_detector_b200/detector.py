@@ -33,7 +33,8 @@ from .weights import resolve as resolve_weights
 
 class HeadDetector:
     def __init__(self, model: str = "vgg_heads_l", image_size: int = 640, *, weights: Union[None, str, Dict[str, torch.Tensor]] = None,
-                 batch_size: int = 1, keep_top_k: int = 100, device_letterbox: bool = True, sparse_heads: bool = True, parity: bool = False):
+                 batch_size: int = 1, keep_top_k: int = 100, device_letterbox: bool = True, sparse_heads: bool = True, parity: bool = False,
+                 act_dtype: Optional[str] = None):
         """`model`, `image_size`: the reference's arguments (detector.py:19).  Keyword-only extensions: `weights` - path to
         `vgg_heads_l.trcd` (the TorchScript blob the reference downloads) / a state_dict checkpoint / a deploy-form dict /
         the literal "synthetic" (default: $VGGHEADS_B200_WEIGHTS; there is no silent fallback to random weights);
@@ -49,6 +50,7 @@ class HeadDetector:
         self._device_letterbox = device_letterbox
         self._sparse_heads = sparse_heads and not parity   # FLAME branch of the heads on the NMS survivors only (same predictions)
         self._parity = parity
+        self._act_dtype = act_dtype   # "fp16" | "bf16" storage of the throughput mode (None: $VGGHEADS_B200_ACT or "fp16")
         self._weights = weights if weights is not None else os.environ.get("VGGHEADS_B200_WEIGHTS")
         self.model = self._read_model(model)
 
@@ -58,7 +60,8 @@ class HeadDetector:
         if model != "vgg_heads_l":
             raise ValueError(f"unknown model {model!r}; only 'vgg_heads_l' (YoloHeads_L) is built")
         w = resolve_weights(self._weights, model)
-        return Engine(w, self._batch, self._image_size, self._keep_top_k, self._flame, sparse_heads=self._sparse_heads, parity=self._parity)
+        return Engine(w, self._batch, self._image_size, self._keep_top_k, self._flame, sparse_heads=self._sparse_heads, parity=self._parity,
+                      act_dtype=self._act_dtype)
 
     # -- host-side pre-processing, same arithmetic as detector.py:32-56
     def _convert_image(self, image) -> np.ndarray:

@@ -18,13 +18,16 @@ class _DevView:
 
 class Engine:
     def __init__(self, weights: Dict[str, torch.Tensor], batch: int, image_size: int = 640, keep_top_k: int = 100,
-                 flame: Optional[FLAMELayer] = None, sparse_heads: Optional[bool] = None, parity: bool = False):
+                 flame: Optional[FLAMELayer] = None, sparse_heads: Optional[bool] = None, parity: bool = False,
+                 act_dtype: Optional[str] = None):
         """`sparse_heads`: run the FLAME branch of the three head levels on 8x8 windows around the NMS survivors
         instead of the whole feature maps (same values at the survivors; the dense [B,A,413] tensor of the
         reference's model boundary then does not exist).  Default: $VGGHEADS_B200_SPARSE_HEADS == "1".
         `parity`: fp32-class conv arithmetic (activations and weights as three bf16 terms, six partial products per MAC
         accumulated in fp32 on the same tensor-core kernels; ~6x the work) for end-to-end checks against the reference's
-        fp32 path.  Dense heads only."""
+        fp32 path.  Dense heads only.
+        `act_dtype`: "fp16" | "bf16" storage of activations and weights in the throughput mode (arch.ACT_DTYPES; default
+        $VGGHEADS_B200_ACT or "fp16").  The parity mode always stores bf16 terms."""
         if not torch.cuda.is_available():
             raise RuntimeError("head_detector_b200.Engine needs a CUDA device (no CPU fallback)")
         self.B, self.S, self.keep_k = int(batch), int(image_size), int(keep_top_k)
@@ -35,7 +38,10 @@ class Engine:
             sparse_heads = os.environ.get("VGGHEADS_B200_SPARSE_HEADS", "0") == "1"
         self.parity = bool(parity)
         self.sparse_heads = bool(sparse_heads) and not self.parity
-        self.plan = arch.build_plan(self.S, sparse_heads=(self.B, self.keep_k) if self.sparse_heads else None, fused_stem=not self.parity)
+        self.act_dtype = "bf16" if self.parity else (act_dtype or arch.default_act_dtype())
+        self._act_torch = arch.ACT_DTYPES[self.act_dtype]
+        self.plan = arch.build_plan(self.S, sparse_heads=(self.B, self.keep_k) if self.sparse_heads else None, fused_stem=not self.parity,
+                                    act_dtype=self.act_dtype)
         if self.parity:
             self.plan = arch.split_plan(self.plan)
         self.packed = arch.pack(self.plan, weights)
@@ -64,6 +70,7 @@ class Engine:
         nd.keep_k = self.keep_k
         nd.n_dense_ops = self.plan.n_dense_ops if self.plan.n_dense_ops is not None else len(self.plan.ops)
         nd.split = 1 if self.parity else 0
+        nd.act_f16 = 1 if self.act_dtype == "fp16" else 0
         h = C.c_void_p()
         _lib.check(_lib.lib().vgh_detector_create(C.byref(nd), self.flame.handle(), C.byref(h)), "vgh_detector_create")
         self._h = h
@@ -205,7 +212,7 @@ class Engine:
         nb = 1 if i in self.plan.stack_bufs else self.B
         arr = np.empty(nb * h * w * c, dtype=np.float32 if fp32 else np.uint16)
         _lib.check(_lib.lib().vgh_detector_read_buffer(self._h, i, arr.ctypes.data, arr.nbytes), "read_buffer")
-        t = torch.from_numpy(arr) if fp32 else torch.from_numpy(arr.view(np.int16)).view(torch.bfloat16).float()
+        t = torch.from_numpy(arr) if fp32 else torch.from_numpy(arr.view(np.int16)).view(self._act_torch).float()
         t = t.reshape(nb, h, w, c)
         if self.parity and not fp32:   # six planes [h|m|h|m|h|l] per 32-channel granule -> y = (l + m) + h
             g = t.reshape(nb, h, w, c // 192, 6, 32)
@@ -213,7 +220,7 @@ class Engine:
         return t
 
     def write_buffer(self, name: str, value: torch.Tensor):
-        """float32 NHWC cpu tensor -> activation buffer `name` (rounded to bf16 unless the buffer is fp32); parity tests."""
+        """float32 NHWC cpu tensor -> activation buffer `name` (rounded to the activation dtype unless the buffer is fp32); parity tests."""
         i = self.plan.buf_names[name]
         h, w, c, fp32 = self.plan.bufs[i]
         nb = 1 if i in self.plan.stack_bufs else self.B
@@ -222,7 +229,7 @@ class Engine:
             hh, mm, ll = arch.split_terms(t.reshape(nb, h, w, c // 192, 1, 32))
             t = torch.cat([hh, mm, hh, mm, hh, ll], dim=4).reshape(nb, h, w, c)
         assert tuple(t.shape) == (nb, h, w, c), (name, tuple(t.shape), (nb, h, w, c))
-        arr = t.numpy() if fp32 else t.to(torch.bfloat16).view(torch.int16).numpy()
+        arr = t.numpy() if fp32 else t.to(self._act_torch).view(torch.int16).numpy()
         _lib.check(_lib.lib().vgh_detector_write_buffer(self._h, i, arr.ctypes.data, arr.nbytes), "write_buffer")
 
     def forward_from(self, first_label: Optional[str]):

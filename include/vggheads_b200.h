@@ -134,7 +134,7 @@ typedef struct {
   int32_t n_bufs, n_ops;
   const vgh_buf_desc* bufs;
   const vgh_op_desc* ops;
-  const uint16_t* weights_host;  /* bf16 bits, all packed conv weights */
+  const uint16_t* weights_host;  /* bf16 (or, with act_f16, fp16) bits, all packed conv weights */
   int64_t n_weights;
   const float* bias_host;
   int64_t n_bias;
@@ -147,6 +147,10 @@ typedef struct {
                                     [h|m|h|m|h|l] per 32-channel granule (buffers carry 6x the channels) and weights are packed
                                     [w_h|w_h|w_m|w_m|w_l|w_h] along K, so that the bf16 MMAs accumulate the six leading partial
                                     products in fp32 (relative error ~2^-22 per product instead of 2^-9).  Dense plan only. */
+  int32_t act_f16;               /* 1: the 16-bit activation buffers and `weights_host` are IEEE fp16 (11 significant bits: the
+                                    precision class of the TF32 convs the reference runs on a GPU by default, and the format the
+                                    released model was trained in - AMP, yolo_heads_l.yaml) instead of bf16 (8 bits); same kernels,
+                                    same tensor-core rate (tcgen05 kind::f16 takes either).  0: bf16.  Must be 0 with `split`. */
 } vgh_net_desc;
 
 int vgh_detector_create(const vgh_net_desc* net, const vgh_flame* flame, vgh_detector** out);

@@ -14,11 +14,18 @@ def bf16_round(t):
     return t.to(torch.bfloat16).to(torch.float32)
 
 
+def act_round(dtype_name):
+    """Rounding of a stored activation for plan.act_dtype ("bf16" | "fp16")."""
+    dt = arch.ACT_DTYPES[dtype_name]
+    return lambda t: t.to(dt).to(torch.float32)
+
+
 def apply_op(pk, op, m, bufs, images_u8=None, emulate_bf16=True, patches=None):
     """Execute ONE plan op on the given NHWC float buffers (in place).  `patches[level]` = list of (image, y, x)
     survivor anchors of head level `level` (1-based) for the sparse-heads ops."""
     P = pk.plan
-    rnd = bf16_round if emulate_bf16 else (lambda t: t)
+    rnd = act_round(P.act_dtype) if emulate_bf16 else (lambda t: t)   # `emulate_bf16`: emulate the 16-bit storage (either format)
+    wdt = arch.ACT_DTYPES[P.act_dtype]
     if op.kind in (_lib.OP_PATCH_GATHER, _lib.OP_PATCH_MASK):
         PT, PC = arch.PATCH, arch.PATCH_C
         sb, so, C = op.src
@@ -48,7 +55,7 @@ def apply_op(pk, op, m, bufs, images_u8=None, emulate_bf16=True, patches=None):
         Bn, _, L = cols.shape
         Ho = images_u8.shape[1] // 2
         cols = cols.view(Bn, 3, 9, L).permute(0, 3, 2, 1).reshape(Bn, Ho, Ho, 27)
-        wts = torch.from_numpy(pk.weights[m["w_off"]:m["w_off"] + m["n_pad"] * 32].view(np.int16).copy()).view(torch.bfloat16).float().reshape(m["n_pad"], 32)
+        wts = torch.from_numpy(pk.weights[m["w_off"]:m["w_off"] + m["n_pad"] * 32].view(np.int16).copy()).view(wdt).float().reshape(m["n_pad"], 32)
         y = cols @ wts[:op.cout, :27].T + torch.from_numpy(pk.bias[m["b_off"]:m["b_off"] + op.cout])
         bufs[op.dst[0]][..., :op.cout] = rnd(F.relu(y) if op.relu else y)
     elif op.kind == _lib.OP_SPP:
@@ -60,7 +67,7 @@ def apply_op(pk, op, m, bufs, images_u8=None, emulate_bf16=True, patches=None):
     else:
         sb, so, cin = op.src
         x = bufs[sb][..., so:so + cin].permute(0, 3, 1, 2)
-        wts = torch.from_numpy(pk.weights[m["w_off"]:m["w_off"] + m["n_pad"] * m["k_total"]].view(np.int16).copy()).view(torch.bfloat16).float()
+        wts = torch.from_numpy(pk.weights[m["w_off"]:m["w_off"] + m["n_pad"] * m["k_total"]].view(np.int16).copy()).view(wdt).float()
         W = wts.reshape(m["n_pad"], op.k, op.k, cin).permute(0, 3, 1, 2)
         bv = torch.from_numpy(pk.bias[m["b_off"]:m["b_off"] + m["n_pad"]])
         y = F.conv2d(x, W, bv, stride=op.stride, padding=op.k // 2)[:, :op.cout]

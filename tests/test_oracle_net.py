@@ -1,6 +1,7 @@
 """Self-consistency of the conv-network oracle (parity unpinned at the super_gradients boundary)
 and of the product's execution plan / weight packing against it - all on CPU."""
 import numpy as np
+import pytest
 import torch
 
 import plan_emulator as pe
@@ -39,15 +40,17 @@ def test_anchor_count_and_order():
     assert pts[0].tolist() == [0.5, 0.5] and pts[1].tolist() == [1.5, 0.5] and pts[80].tolist() == [0.5, 1.5]
 
 
-def test_plan_and_packing_reproduce_oracle():
-    """Interpret the product's plan with its packed bf16 weights on CPU; compare with the oracle."""
+@pytest.mark.parametrize("act_dtype", ["bf16", "fp16"])
+def test_plan_and_packing_reproduce_oracle(act_dtype):
+    """Interpret the product's plan with its packed 16-bit weights (either storage format) on CPU; compare with the oracle."""
     S = 128
     w = no.synthetic_weights(3)
-    pk = arch.pack(arch.build_plan(S), w)
+    pk = arch.pack(arch.build_plan(S, act_dtype=act_dtype), w)
+    dt = arch.ACT_DTYPES[act_dtype]
     torch.manual_seed(0)
     img = torch.randint(0, 256, (2, S, S, 3), dtype=torch.uint8)
-    wq = {k: (v.to(torch.bfloat16).float() if k.endswith(".w") else v) for k, v in w.items()}
-    wq["stem.w"] = (w["stem.w"] / 255.0).to(torch.bfloat16).float() * 255.0  # the packed stem weights carry the /255
+    wq = {k: (v.to(dt).float() if k.endswith(".w") else v) for k, v in w.items()}
+    wq["stem.w"] = (w["stem.w"] / 255.0).to(dt).float() * 255.0  # the packed stem weights carry the /255
     taps = {}
     with torch.no_grad():
         no.DeployNet(wq).forward(img.permute(0, 3, 1, 2).float() / 255, taps)
