@@ -46,11 +46,11 @@ def _peaks():
 
 def ncu_conv_traffic(dense_heads=False, batch=PER_GPU_BATCH):
     """DRAM bytes moved by the conv_igemm launches of ONE step (dram__bytes_read+write summed over the
-    launches) from the committed ncu launch list of the same workload (profiles/r2_ncu_launches.csv: batch 64, sparse
+    launches) from the committed ncu launch list of the same workload (profiles/r2b_ncu_launches.csv: batch 64, sparse
     heads); None when no list of this configuration is committed."""
     import csv
 
-    path = os.path.join(ROOT, "profiles", "r2_ncu_launches.csv")
+    path = os.path.join(ROOT, "profiles", "r2b_ncu_launches.csv")
     if dense_heads or batch != 64 or not os.path.exists(path):
         return None
     tot = 0.0
@@ -515,7 +515,7 @@ def run_ours(args, rank, world, local_rank):
                 "frac_note": "frac = frac_serial: executed FLOPs / summed event durations of the conv launches in a serial eager pass; "
                              "frac_step: the same FLOPs / ms_per_step of the timed CUDA-graph region (all kernels of the step, two batches overlapping)",
                 "peak_source": pk["src"], "traffic": ncu_conv_traffic(args.dense_heads, B),
-                "traffic_note": "DRAM bytes of all conv_igemm launches of one step from the committed ncu launch list (profiles/r2_ncu_launches.csv, batch 64); layer-minimal activation bytes are 0.415 GB/image (SURVEY 8d): activations that fit L2 are consumed from L2",
+                "traffic_note": "DRAM bytes of all conv_igemm launches of one step from the committed ncu launch list (profiles/r2b_ncu_launches.csv, batch 64); layer-minimal activation bytes are 0.415 GB/image (SURVEY 8d): activations that fit L2 are consumed from L2",
                 "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_ms / all_ms,
                 "algorithmic_flops_per_step": conv_flops}
         parity = parity_check(eng, boxes, scores, B)
