@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
   // (PAIR: this CTA's half of the tile, th/2 rows + halo)
   const uint32_t x_bytes = static_cast<uint32_t>(PAIR ? p.tw * (p.th / 2 + 2) : XR ? p.tw * (p.th + 2) : npix) * kRowBytes;
   const uint32_t x_slot = (x_bytes + 1023u) & ~1023u;
-  const int ks = XR ? 1 : p.ks;                                     // k-blocks per pipeline stage (one barrier round trip)
+  const int ks = p.ks;                                              // k-blocks per pipeline stage (one barrier round trip); XR: 1, or 3 = the three row taps of a column shift share a stage
   const int x_slots = XR ? p.xslots : p.stages * ks;               // XR: the pixel tiles have their own (shallower) ring
   const uint32_t w_base = smem_base;
   const uint32_t x_base = w_base + p.stages * ks * kWBytes;
@@ -240,13 +240,24 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
                 xs = 0;
                 xphase ^= 1;
               }
-              for (int dy = 0; dy < 3; ++dy) {
+              if (ks == 3) {   // one stage = the weight k-blocks of the three row taps: a third of the barrier round trips
                 mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-                mbar_arrive_expect_tx(full_bar + 8 * stage, w_tx);
-                load_w(w_base + stage * kWBytes, full_bar + 8 * stage, (dy * 3 + dx) * p.cin + cb * BK, n_base);
+                mbar_arrive_expect_tx(full_bar + 8 * stage, 3 * w_tx);
+                for (int dy = 0; dy < 3; ++dy)
+                  load_w(w_base + (stage * 3 + dy) * kWBytes, full_bar + 8 * stage, (dy * 3 + dx) * p.cin + cb * BK, n_base);
                 if (++stage == p.stages) {
                   stage = 0;
                   phase ^= 1;
+                }
+              } else {
+                for (int dy = 0; dy < 3; ++dy) {
+                  mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                  mbar_arrive_expect_tx(full_bar + 8 * stage, w_tx);
+                  load_w(w_base + stage * kWBytes, full_bar + 8 * stage, (dy * 3 + dx) * p.cin + cb * BK, n_base);
+                  if (++stage == p.stages) {
+                    stage = 0;
+                    phase ^= 1;
+                  }
                 }
               }
             }
@@ -294,6 +305,25 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
           for (int g = 0; g < 3 * cblks; ++g) {
             mbar_wait(xfull_bar + 8 * xs, xphase);
             tc_fence_after();
+            if (!PAIR && ks == 3) {   // the three row taps share one weight stage
+              mbar_wait(full_bar + 8 * stage, phase);
+              tc_fence_after();
+              for (int dy = 0; dy < 3; ++dy) {
+                const uint64_t w_desc = umma_smem_desc(w_base + (stage * 3 + dy) * kWBytes, kRowBytes);
+                const uint64_t x_desc = umma_smem_desc(x_base + xs * x_slot + dy * dy_bytes, kRowBytes);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                  umma_bf16(d, w_desc + 2 * k, x_desc + 2 * k, idesc, accumulate);
+                  accumulate = 1u;
+                }
+              }
+              if (n_cl > 1) umma_commit_mc(empty_bar + 8 * stage, mc_mask);
+              else umma_commit(empty_bar + 8 * stage);
+              if (++stage == p.stages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            } else {
             for (int dy = 0; dy < 3; ++dy) {
               mbar_wait(full_bar + 8 * stage, phase);
               tc_fence_after();
@@ -312,6 +342,7 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
                 stage = 0;
                 phase ^= 1;
               }
+            }
             }
             // all three row taps of this pixel tile have been issued
             if (PAIR) umma_commit_2cta_mc(xempty_bar + 8 * xs, 3); else umma_commit(xempty_bar + 8 * xs);
@@ -381,6 +412,18 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
       int b_img, h0, w0, n_base;
       const bool valid = item_coords(item, b_img, h0, w0, n_base);
       const float bias = ch_ok ? __ldg(p.bias + n_base + ch) : 0.f;
+      // two staging tiles: the residual tile of the NEXT item is fetched into the other tile while this item is still being
+      // multiplied (its previous user, the store of item i-1, only has to have been read out)
+      if (has_res && stg_bufs == 2 && epi_lead) {
+        const int next = item + n_cls;
+        if (next < n_citems) {
+          tma_store_wait_read();
+          int nb, nh, nw, nn;
+          item_coords(next, nb, nh, nw, nn);
+          mbar_arrive_expect_tx(res_full_bar + 8 * (sb ^ 1), stage_bytes);
+          tma_load_4d(stage_base + (sb ^ 1) * stage_slot, &p.tmRes, res_full_bar + 8 * (sb ^ 1), p.res_coff + nn, nw, nh, nb);
+        }
+      }
       mbar_wait(tmem_full_bar + 8 * acc, acc_phase);
       tc_fence_after();
       if (has_res) {
@@ -426,7 +469,7 @@ __global__ void __launch_bounds__(kSwapThreads, 1) conv_igemm_swap_kernel(const 
         // the tile the NEXT item writes must have been read out by its previous store
         if (stg_bufs == 2) tma_store_wait_read_keep1(); else tma_store_wait_read();
         const int next = item + n_cls;
-        if (has_res && next < n_citems) {
+        if (has_res && stg_bufs == 1 && next < n_citems) {
           int nb, nh, nw, nn;
           item_coords(next, nb, nh, nw, nn);
           mbar_arrive_expect_tx(res_full_bar + 8 * nsb, stage_bytes);
@@ -459,7 +502,7 @@ size_t conv_swap_smem_bytes(const ConvLaunch& L, int bk) {
   const size_t staging = (static_cast<size_t>(L.tw * L.th) * L.gw * (L.out_fp32 ? 4 : 2) + 1023) & ~static_cast<size_t>(1023);
   if (L.xr) {
     const size_t x_slot = (static_cast<size_t>(L.tw * (L.pair ? L.th / 2 + 2 : L.th + 2)) * bk * 2 + 1023) & ~static_cast<size_t>(1023);
-    return 1024 + static_cast<size_t>(L.stages) * 128 * bk * 2 + L.xslots * x_slot + L.stg_bufs * staging + 16 * L.stages + 256;
+    return 1024 + static_cast<size_t>(L.stages) * L.ks * 128 * bk * 2 + L.xslots * x_slot + L.stg_bufs * staging + 16 * L.stages + 256;
   }
   const size_t x_slot = (static_cast<size_t>(L.tw * L.th) * bk * 2 + 1023) & ~static_cast<size_t>(1023);
   return 1024 + static_cast<size_t>(L.stages) * L.ks * (128 * bk * 2 + x_slot) + L.stg_bufs * staging + 16 * L.stages + 256;
@@ -515,7 +558,7 @@ int conv_swap_launch(const ConvLaunch& L, int bk, int sms, cudaStream_t stream, 
     return 7;
   }
   if (L.xr) {
-    if (L.ntaps != 9 || L.stride != 1 || L.tw % 8 || L.xslots < 2 || L.xslots > 8 || L.stages < 2) {
+    if (L.ntaps != 9 || L.stride != 1 || L.tw % 8 || L.xslots < 2 || L.xslots > 8 || L.stages < 2 || (L.ks != 1 && (L.ks != 3 || L.pair))) {
       snprintf(err, errlen, "swap conv: launch not eligible for the tap-reuse variant (taps %d stride %d tile %dx%d xslots %d stages %d)",
                L.ntaps, L.stride, L.tw, L.th, L.xslots, L.stages);
       return 7;

@@ -10,11 +10,20 @@
 // is rounded once to fp32, and the remaining ops (R*v, *scale, +t, -pad, /scale) are done in fp32
 // in the reference's operation order with non-contracted intrinsics so that roundings coincide.
 //
-// Work decomposition: item = 128 vertices x (8*HG heads), persistent CTAs walk the items.  Each thread owns one vertex (3 coords) for
-// 8 heads = 24 fp64 accumulators.  The shape basis slab of the CTA's 128 vertices streams through a
-// 4-stage cp.async pipeline (8 coefficients per stage) as fp32 - the precision the reference holds it
-// in - and is widened exactly to fp64 in registers; it is shared by the HG head groups.  Betas live in
-// shared memory as fp64 and are read as broadcast 128-bit loads.
+// Work decomposition: item = 128 vertices x (8*HG heads), persistent CTAs walk the items.  The blendshape sum is a small
+// fp64 GEMM per item - [8*HG heads x K] (betas) x [K x 384 vertex coordinates] (basis slab), K = live coefficients + 9 pose
+// rows - and runs on the FP64 tensor pipe: mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4), heads on M, vertex coordinates on N.
+// Round 1/2 used one DFMA per (head, coordinate, coefficient): 24 DFMA + 7 LDS + 3 F2F per thread and coefficient issue at
+// most 44 FMA/clk/SM (profiles/r2b_fp64_rate_probe.txt) and the kernel reached 25; DMMA sustains 62-66 FMA/clk/SM (= the
+// B200's 37 TFLOP/s FP64 peak) with a fifth of the instructions.  Same arithmetic class: fp64 products and sums.
+// Each warp owns 48/(4*HG) n-tiles x HG m-tiles = 12 accumulator tiles (24 doubles per thread) and streams ITS OWN slice of
+// the basis slab (its 48 or 96 coordinates x 8 coefficients per stage) through a private 3-stage cp.async pipeline: the B
+// operand is not shared between warps, so the main loop needs no CTA-wide barrier at all (cp.async.wait_group + __syncwarp)
+// and the warps of the three resident CTAs drift apart instead of hitting the FP64 tensor pipe in lock step.  The basis
+// stays fp32 - the precision the reference holds it in - and is widened exactly to fp64 when a B fragment is loaded; so are
+// the betas (fp32 parameters).  Row pitches are padded so that the fragment loads (4 rows x 8 consecutive elements per warp)
+// are bank-conflict free.  For the per-vertex epilogue (skinning needs x, y, z of a vertex in one thread) the accumulators
+// cross shared memory once per m-tile.
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -36,6 +45,8 @@ constexpr int kHPT = 8;   // heads per thread
 constexpr int kLc = 8;    // coefficients per pipeline stage
 constexpr int kNS = 3;    // pipeline stages of the basis stream (3 x 12 KB: three CTAs per SM fit, ncu: the kernel is latency-, not bandwidth-bound)
 constexpr int kNPose = 9; // live pose-corrective rows (jaw joint only)
+constexpr int kNC = kTileV * 3;       // vertex coordinates per item = GEMM N
+constexpr int kXPitch = kNC + 8;      // fp64 row pitch of the accumulator exchange tile: rows 16 banks apart
 constexpr int kParams = 413;
 
 struct FlameDev {
@@ -68,6 +79,17 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// shared-memory geometry, used by the kernel and by the host-side size computation
+__host__ __device__ constexpr int flame_beta_pitch(int heads) { return heads == 8 ? 8 : heads + 8; }
+__host__ __device__ constexpr int flame_stage_floats(int heads) {   // all warps' private basis stages
+  return (heads / 2) * kNS * kLc * ((kNC / 8) / (heads / 2) * 8 + 8);
+}
+
+// D[8x8] += A[8x4] * B[4x8] in fp64 (DMMA.8x8x4).  Lane l holds a[l>>2][l&3], b[l&3][l>>2], d[l>>2][2*(l&3) + {0,1}].
+__device__ __forceinline__ void dmma_884(double (&d)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
 }
 
 // rot6d -> rotation matrix, reference op order (utils.py:120-128; F.normalize eps 1e-12), fp32.
@@ -117,7 +139,16 @@ __device__ void rodrigues_f32(const float* r, float* R) {
 
 template <int HG>
 __global__ void __launch_bounds__(kTileV* HG, HG == 1 ? 4 : 3) flame_decode_kernel(const FlameArgs a) {
-  constexpr int kHeads = kHPT * HG;
+  constexpr int kHeads = kHPT * HG;       // heads per item = HG m-tiles of 8
+  constexpr int kBP = flame_beta_pitch(kHeads);   // fp32 row pitch of the beta table: rows 8 banks apart -> conflict-free A fragments
+  constexpr int kWarps = 4 * HG;
+  constexpr int kNT = (kNC / 8) / kWarps; // n-tiles (8 coordinates) per warp: 6 (HG = 2) or 12 (HG = 1)
+  constexpr int kWP = kNT * 8 + 8;        // fp32 row pitch of a warp's basis stage: rows 8 / 24 banks apart -> conflict-free B fragments
+  constexpr int kWStage = kLc * kWP;      // floats per stage of one warp
+  static_assert(kNT * kWarps * 8 == kNC, "n-tiles must split evenly over the warps");
+  static_assert(kWP % 32 == 8 || kWP % 32 == 24, "B-fragment rows must be 8 banks apart");
+  static_assert(kBP % 32 == 8 || kBP % 32 == 24, "A-fragment rows must be 8 banks apart");
+  static_assert(kWarps * kNS * kWStage == flame_stage_floats(kHeads), "host-side shared-memory size out of step");
   const int n_heads = a.n_dev ? min(*a.n_dev, a.n) : a.n;
   // work items = (vertex tile, head group); CTAs walk them with a grid stride so that the device-side
   // head count decides the amount of work, not the (capacity-sized) launch
@@ -126,21 +157,23 @@ __global__ void __launch_bounds__(kTileV* HG, HG == 1 ? 4 : 3) flame_decode_kern
   const int tid = threadIdx.x;
   const int vl = tid % kTileV;
   const int grp = tid / kTileV;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int fr = lane >> 2, fc = lane & 3;   // fragment coordinates: A[fr][fc], B[fc][fr], D[fr][2*fc + {0,1}]
   const int lb = a.ns + a.ne;          // live blendshape coefficients
   const int lt = lb + kNPose;          // + pose-corrective rows
   const int n_chunks = (lt + kLc - 1) / kLc;
   const int lt_pad = n_chunks * kLc;
 
   extern __shared__ __align__(16) uint8_t smem[];
-  float* sd_s = reinterpret_cast<float*>(smem);                         // [kNS][kLc][128][3] fp32
-  double* beta_s = reinterpret_cast<double*>(sd_s + kNS * kLc * kTileV * 3);  // [lt_pad][kHeads]
-  double* tj_s = beta_s + static_cast<size_t>(lt_pad) * kHeads;         // [kHeads][3]
+  float* sd_s = reinterpret_cast<float*>(smem);                         // [kWarps][kNS][kLc][kWP] fp32: private stages of every warp
+  double* tj_s = reinterpret_cast<double*>(sd_s + kWarps * kNS * kWStage);    // [kHeads][3]
   double* r2_s = tj_s + kHeads * 3;                                     // [kHeads][9]
   float* R_s = reinterpret_cast<float*>(r2_s + kHeads * 9);             // [kHeads][9]
   float* st_s = R_s + kHeads * 9;                                       // [kHeads][8]: scale,tx,ty,tz,padx,pady,iscale
-  // [3][400] jaw-joint regressor x shape basis: only read in the prologue, so it borrows the (idle) basis stage buffers
-  double* js2_s = reinterpret_cast<double*>(sd_s);
-  static_assert(3 * kL * sizeof(double) <= kNS * kLc * kTileV * 3 * sizeof(float), "js2 must fit the stage buffers");
+  float* beta_s = st_s + kHeads * 8;                                    // [lt_pad][kBP] fp32 (the parameters' own precision)
+  // the accumulator exchange tile [8 heads][kXPitch] of the epilogue borrows the (by then drained) basis stage buffers
+  double* x_s = reinterpret_cast<double*>(sd_s);
+  static_assert(8 * kXPitch * sizeof(double) <= kWarps * kNS * kWStage * sizeof(float), "the exchange tile must fit the stage buffers");
   // items are ordered head-group-major and every CTA takes a CONTIGUOUS range of them, so that the per-head-group
   // prologue (betas to fp64, Rodrigues, 6D rotation, jaw-joint regression: a 192..400-term dependent chain) runs once per
   // head group a CTA touches instead of once per (vertex tile, head group)
@@ -153,16 +186,44 @@ __global__ void __launch_bounds__(kTileV* HG, HG == 1 ? 4 : 3) flame_decode_kern
   const bool fresh = head0 != prologue_head0;   // uniform across the CTA
   prologue_head0 = head0;
 
-  // ---- prologue: betas (fp64), per-head rotations
+  // ---- the basis stream of this item starts first: its latency overlaps the prologue
+  const int n_warp0 = warp * (kNT * 8);   // first coordinate of this warp's n-tiles
+  float* wst = sd_s + warp * (kNS * kWStage);          // this warp's stages
+  const uint32_t wst_smem = static_cast<uint32_t>(__cvta_generic_to_shared(wst));
+  constexpr int kVecPerRow = kNT * 8 * 4 / 16;          // 16-byte vectors of one coefficient row of the warp's slice (12 | 24)
+  constexpr int kVecPerStage = kLc * kVecPerRow;        // 96 | 192: 3 | 6 per lane
+  auto issue = [&](int chunk) {
+    if (chunk < n_chunks) {
+      const int buf = chunk % kNS;
+#pragma unroll
+      for (int q = lane; q < kVecPerStage; q += 32) {
+        const int row = q / kVecPerRow;
+        const int off = q - row * kVecPerRow;
+        const int i = chunk * kLc + row;
+        const float* src;
+        if (i < lb) {
+          const int l = i < a.ns ? i : 300 + (i - a.ns);
+          src = a.c.sdt + (static_cast<size_t>(l) * kVPad + v0) * 3;
+        } else {
+          const int m = min(i - lb, kNPose - 1);  // rows past the end multiply a zero beta
+          src = a.c.pd + (static_cast<size_t>(m) * kVPad + v0) * 3;
+        }
+        cp_async16(wst_smem + (buf * kWStage + row * kWP) * 4 + off * 16, src + n_warp0 + off * 4);
+      }
+    }
+    cp_async_commit();  // (possibly empty) one group per chunk keeps the wait arithmetic uniform
+  };
+  for (int c = 0; c < kNS - 1; ++c) issue(c);   // (the previous item's reads of the exchange tile are behind its closing barrier)
+
+  // ---- prologue: betas, per-head rotations
   if (fresh) {
-  for (int i = tid; i < 3 * kL; i += blockDim.x) js2_s[i] = a.c.js2[i];  // (the previous item's last basis reads are behind a barrier)
   for (int idx = tid; idx < lb * kHeads; idx += blockDim.x) {
     const int h = idx / lb, i = idx - h * lb;
     const int l = i < a.ns ? i : 300 + (i - a.ns);
     const int hg = head0 + h;
-    beta_s[i * kHeads + h] = hg < n_heads ? static_cast<double>(a.params[static_cast<size_t>(hg) * kParams + l]) : 0.0;
+    beta_s[i * kBP + h] = hg < n_heads ? a.params[static_cast<size_t>(hg) * kParams + l] : 0.f;
   }
-  for (int idx = tid; idx < (lt_pad - lt) * kHeads; idx += blockDim.x) beta_s[lt * kHeads + idx] = 0.0;
+  for (int idx = tid; idx < (lt_pad - lt) * kHeads; idx += blockDim.x) beta_s[(lt + idx / kHeads) * kBP + idx % kHeads] = 0.f;
   if (tid < kHeads) {
     const int hg = head0 + tid;
     float R2[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
@@ -182,23 +243,25 @@ __global__ void __launch_bounds__(kTileV* HG, HG == 1 ? 4 : 3) flame_decode_kern
       R_s[tid * 9 + i] = R[i];
       // pose feature = (R2 - I) in fp32, as the reference forms it, acts as 9 extra "betas"
       const float id = (i == 0 || i == 4 || i == 8) ? 1.f : 0.f;
-      beta_s[(lb + i) * kHeads + tid] = static_cast<double>(__fsub_rn(R2[i], id));
+      beta_s[(lb + i) * kBP + tid] = __fsub_rn(R2[i], id);
     }
     st_s[tid * 8 + 0] = sc; st_s[tid * 8 + 1] = t[0]; st_s[tid * 8 + 2] = t[1]; st_s[tid * 8 + 3] = t[2];
     st_s[tid * 8 + 4] = xf[0]; st_s[tid * 8 + 5] = xf[1]; st_s[tid * 8 + 6] = xf[2];
   }
   __syncthreads();
-  // jaw joint J2 = J2_template + JS2 . beta ; tJ = J2 - R2 . J2.  Four lanes share one (head, coord)
-  // dot product so the 192..400-term chain of dependent L2 loads is four times shorter.
+  // jaw joint J2 = J2_template + JS2 . beta ; tJ = J2 - R2 . J2.  Four lanes share one (head, coord) dot product so the
+  // 192..400-term chain is four times shorter; the [3][400] regressor x basis table is read straight from L2 (its loads
+  // do not depend on the chain, so they pipeline).
   {
     const int o = tid >> 2, part = tid & 3;
     const bool live = o < kHeads * 3;
     const int h = live ? o / 3 : 0, k = live ? o - h * 3 : 0;
     double acc = 0.0;
     if (live) {
+#pragma unroll 8
       for (int i = part; i < lb; i += 4) {
         const int l = i < a.ns ? i : 300 + (i - a.ns);
-        acc = fma(js2_s[k * kL + l], beta_s[i * kHeads + h], acc);
+        acc = fma(__ldg(a.c.js2 + k * kL + l), static_cast<double>(beta_s[i * kBP + h]), acc);
       }
     }
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
@@ -215,102 +278,84 @@ __global__ void __launch_bounds__(kTileV* HG, HG == 1 ? 4 : 3) flame_decode_kern
     tj_s[tid * 3] = o0; tj_s[tid * 3 + 1] = o1; tj_s[tid * 3 + 2] = o2;
   }
   }  // fresh head group
-  // (visibility of tj_s to everyone is guaranteed by the __syncthreads inside the main loop)
+  __syncthreads();   // tj_s / beta_s of a fresh head group are complete for every warp (the main loop has no CTA-wide barrier)
 
-  // ---- main loop: acc[h][k] = template + sum_i beta[h][i] * basis[i][v][k]
-  double acc[kHPT][3];
-  {
-    const double t0 = a.c.vt[(v0 + vl) * 3], t1 = a.c.vt[(v0 + vl) * 3 + 1], t2 = a.c.vt[(v0 + vl) * 3 + 2];
+  // ---- main loop: acc[head][coord] = template[coord] + sum_i beta[head][i] * basis[i][coord], as D += A * B tiles
+  double acc[HG][kNT][2];
 #pragma unroll
-    for (int h = 0; h < kHPT; ++h) { acc[h][0] = t0; acc[h][1] = t1; acc[h][2] = t2; }
+  for (int j = 0; j < kNT; ++j) {
+    const double2 t = *reinterpret_cast<const double2*>(a.c.vt + static_cast<size_t>(v0) * 3 + n_warp0 + j * 8 + 2 * fc);
+#pragma unroll
+    for (int m = 0; m < HG; ++m) { acc[m][j][0] = t.x; acc[m][j][1] = t.y; }
   }
-  const uint32_t sd_smem = static_cast<uint32_t>(__cvta_generic_to_shared(sd_s));
-  constexpr int kRowBytes = kTileV * 3 * 4;            // 1536 B per coefficient row (fp32)
-  constexpr int kStageBytes = kLc * kRowBytes;         // 12288 B
-  constexpr int kVecPerStage = kStageBytes / 16;       // 768
-  auto issue = [&](int chunk) {
-    if (chunk < n_chunks) {
-      const int buf = chunk % kNS;
-      for (int q = tid; q < kVecPerStage; q += blockDim.x) {
-        const int row = q / (kRowBytes / 16);
-        const int off = q - row * (kRowBytes / 16);
-        const int i = chunk * kLc + row;
-        const float* src;
-        if (i < lb) {
-          const int l = i < a.ns ? i : 300 + (i - a.ns);
-          src = a.c.sdt + (static_cast<size_t>(l) * kVPad + v0) * 3;
-        } else {
-          const int m = min(i - lb, kNPose - 1);  // rows past the end multiply a zero beta
-          src = a.c.pd + (static_cast<size_t>(m) * kVPad + v0) * 3;
-        }
-        cp_async16(sd_smem + buf * kStageBytes + row * kRowBytes + off * 16, reinterpret_cast<const uint8_t*>(src) + off * 16);
-      }
-    }
-    cp_async_commit();  // (possibly empty) one group per chunk keeps the wait arithmetic uniform
-  };
-  for (int c = 0; c < kNS - 1; ++c) issue(c);
   for (int c = 0; c < n_chunks; ++c) {
-    cp_async_wait<kNS - 2>();  // chunk c has landed (groups complete in order)
-    __syncthreads();           // ... for every thread; and the buffer of chunk c-1 is free again
+    cp_async_wait<kNS - 2>();  // this lane's copies of chunk c have landed (groups complete in order)
+    __syncwarp();              // ... every lane's; and every lane is done reading the buffer of chunk c-1, which is refilled next
     issue(c + kNS - 1);
-    const float* sd = sd_s + (c % kNS) * (kLc * kTileV * 3) + vl * 3;
-    const double* bt = beta_s + static_cast<size_t>(c) * kLc * kHeads + grp * kHPT;
+    const float* sd = wst + (c % kNS) * kWStage + fc * kWP + fr;    // B[fc][fr] of n-tile 0, k-step 0
+    const float* bt = beta_s + (c * kLc + fc) * kBP + fr;           // A[fr][fc] of m-tile 0, k-step 0
 #pragma unroll
-    for (int r = 0; r < kLc; ++r) {
-      const double s0 = static_cast<double>(sd[r * kTileV * 3]), s1 = static_cast<double>(sd[r * kTileV * 3 + 1]),
-                   s2 = static_cast<double>(sd[r * kTileV * 3 + 2]);
-      const double2* b2 = reinterpret_cast<const double2*>(bt + r * kHeads);
+    for (int ks = 0; ks < kLc / 4; ++ks) {
+      double af[HG];
 #pragma unroll
-      for (int hh = 0; hh < kHPT / 2; ++hh) {
-        const double2 b = b2[hh];
-        acc[2 * hh][0] = fma(s0, b.x, acc[2 * hh][0]);
-        acc[2 * hh][1] = fma(s1, b.x, acc[2 * hh][1]);
-        acc[2 * hh][2] = fma(s2, b.x, acc[2 * hh][2]);
-        acc[2 * hh + 1][0] = fma(s0, b.y, acc[2 * hh + 1][0]);
-        acc[2 * hh + 1][1] = fma(s1, b.y, acc[2 * hh + 1][1]);
-        acc[2 * hh + 1][2] = fma(s2, b.y, acc[2 * hh + 1][2]);
+      for (int m = 0; m < HG; ++m) af[m] = static_cast<double>(bt[ks * 4 * kBP + m * 8]);
+#pragma unroll
+      for (int j = 0; j < kNT; ++j) {
+        const double bf = static_cast<double>(sd[ks * 4 * kWP + j * 8]);
+#pragma unroll
+        for (int m = 0; m < HG; ++m) dmma_884(acc[m][j], af[m], bf);
       }
     }
   }
   cp_async_wait<0>();
-  __syncthreads();
+  __syncthreads();   // every warp is done with its stage buffers: together they become the exchange tile
 
-  // ---- epilogue: skinning + rigid transform, per head
+  // ---- epilogue: skinning + rigid transform.  Per m-tile the accumulators cross shared memory ([8 heads][coordinate]) so
+  // that thread (vertex vl, group grp) holds x, y, z of its vertex for 8 / HG heads
   const int v = v0 + vl;
-  if (v < kV) {
-  const double wi = a.c.wI[v], w2 = a.c.w2[v];
+  const double wi = a.c.wI[v], w2 = a.c.w2[v];   // (padded vertices: zeros)
 #pragma unroll
-  for (int h = 0; h < kHPT; ++h) {
-    const int hl = grp * kHPT + h;
-    const int hg = head0 + hl;
-    if (hg >= n_heads) break;
-    const double* r2 = r2_s + hl * 9;
-    const double x = acc[h][0], y = acc[h][1], z = acc[h][2];
-    const double rx = r2[0] * x + r2[1] * y + r2[2] * z + tj_s[hl * 3];
-    const double ry = r2[3] * x + r2[4] * y + r2[5] * z + tj_s[hl * 3 + 1];
-    const double rz = r2[6] * x + r2[7] * y + r2[8] * z + tj_s[hl * 3 + 2];
-    const float mx = static_cast<float>(wi * x + w2 * rx);
-    const float my = static_cast<float>(wi * y + w2 * ry);
-    const float mz = __fadd_rn(static_cast<float>(wi * z + w2 * rz), 0.05f);  // flame.py:164
-    const size_t o = (static_cast<size_t>(hg) * kV + v) * 3;
-    if (a.verts) { a.verts[o] = mx; a.verts[o + 1] = my; a.verts[o + 2] = mz; }
-    const float* R = R_s + hl * 9;
-    const float* st = st_s + hl * 8;
-    float out[3];
+  for (int m = 0; m < HG; ++m) {
+    if (m) __syncthreads();   // the previous m-tile has been read
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      float rv = __fmul_rn(R[i * 3], mx);
-      rv = __fmaf_rn(R[i * 3 + 1], my, rv);
-      rv = __fmaf_rn(R[i * 3 + 2], mz, rv);
-      out[i] = __fadd_rn(__fmul_rn(rv, st[0]), st[1 + i]);  // flame.py:198-199
+    for (int j = 0; j < kNT; ++j)
+      *reinterpret_cast<double2*>(x_s + fr * kXPitch + n_warp0 + j * 8 + 2 * fc) = make_double2(acc[m][j][0], acc[m][j][1]);
+    __syncthreads();
+    if (v < kV) {
+#pragma unroll
+      for (int hs = 0; hs < kHPT / HG; ++hs) {
+        const int hx = grp * (kHPT / HG) + hs;   // head inside the m-tile
+        const int hl = m * 8 + hx;
+        const int hg = head0 + hl;
+        if (hg >= n_heads) break;
+        const double* r2 = r2_s + hl * 9;
+        const double x = x_s[hx * kXPitch + vl * 3], y = x_s[hx * kXPitch + vl * 3 + 1], z = x_s[hx * kXPitch + vl * 3 + 2];
+        const double rx = r2[0] * x + r2[1] * y + r2[2] * z + tj_s[hl * 3];
+        const double ry = r2[3] * x + r2[4] * y + r2[5] * z + tj_s[hl * 3 + 1];
+        const double rz = r2[6] * x + r2[7] * y + r2[8] * z + tj_s[hl * 3 + 2];
+        const float mx = static_cast<float>(wi * x + w2 * rx);
+        const float my = static_cast<float>(wi * y + w2 * ry);
+        const float mz = __fadd_rn(static_cast<float>(wi * z + w2 * rz), 0.05f);  // flame.py:164
+        const size_t o = (static_cast<size_t>(hg) * kV + v) * 3;
+        if (a.verts) { a.verts[o] = mx; a.verts[o + 1] = my; a.verts[o + 2] = mz; }
+        const float* R = R_s + hl * 9;
+        const float* st = st_s + hl * 8;
+        float out[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          float rv = __fmul_rn(R[i * 3], mx);
+          rv = __fmaf_rn(R[i * 3 + 1], my, rv);
+          rv = __fmaf_rn(R[i * 3 + 2], mz, rv);
+          out[i] = __fadd_rn(__fmul_rn(rv, st[0]), st[1 + i]);  // flame.py:198-199
+        }
+        out[0] = __fsub_rn(out[0], st[4]);  // detector.py:67-69
+        out[1] = __fsub_rn(out[1], st[5]);
+        a.proj[o] = __fdiv_rn(out[0], st[6]);
+        a.proj[o + 1] = __fdiv_rn(out[1], st[6]);
+        a.proj[o + 2] = __fdiv_rn(out[2], st[6]);
+      }
     }
-    out[0] = __fsub_rn(out[0], st[4]);  // detector.py:67-69
-    out[1] = __fsub_rn(out[1], st[5]);
-    a.proj[o] = __fdiv_rn(out[0], st[6]);
-    a.proj[o + 1] = __fdiv_rn(out[1], st[6]);
-    a.proj[o + 2] = __fdiv_rn(out[2], st[6]);
   }
-  }  // v < kV
   __syncthreads();  // shared memory is reused by the next work item
   }  // item loop
 }
@@ -322,9 +367,8 @@ struct FlameModel {
 };
 
 static size_t flame_smem_bytes(int heads, int lt_pad) {
-  return sizeof(float) * (kNS * kLc * kTileV * 3) +
-         sizeof(double) * (static_cast<size_t>(lt_pad) * heads + heads * 3 + heads * 9) +
-         sizeof(float) * (heads * 9 + heads * 8);
+  return sizeof(float) * flame_stage_floats(heads) + sizeof(double) * (heads * 3 + heads * 9) + sizeof(float) * (heads * 9 + heads * 8) +
+         sizeof(float) * static_cast<size_t>(lt_pad) * flame_beta_pitch(heads);
 }
 
 int flame_model_create(const float* v_template, const float* shapedirs, const float* posedirs, const float* j_regressor,

@@ -276,6 +276,18 @@ static bool deep_rings() {
   const char* e = getenv("VGGHEADS_B200_DEEP_RINGS");
   return !(e && e[0] == '0');
 }
+// tap-reuse kernel, 32-channel K blocks: the three row taps of a column shift share one weight stage (default and
+// autotune candidate); VGGHEADS_B200_WGROUP = 0: one tap per stage as for the 64-channel K blocks (A/B aid)
+static bool wgroup_default() {
+  const char* e = getenv("VGGHEADS_B200_WGROUP");
+  return !(e && e[0] == '0');
+}
+// tap-reuse kernel, residual layers with 32-channel K blocks: second staging tile = residual prefetch one item ahead;
+// VGGHEADS_B200_STG2 = 0 keeps one tile (A/B aid)
+static bool stg2_default() {
+  const char* e = getenv("VGGHEADS_B200_STG2");
+  return !(e && e[0] == '0');
+}
 // test aid: VGGHEADS_B200_SWAP=1 makes the un-tuned heuristic pick the swapped kernel for every eligible op
 // (by default only large maps with Cout <= 128 do), so that small parity cases exercise it everywhere
 static bool swap_forced() {
@@ -389,15 +401,20 @@ static int build_conv(vgh_detector* d, OpRt& o) {
   if (L.swap && L.xr) {
     // two rings: pixel tiles with halo rows (xslots deep) and weight k-blocks (`stages` deep)
     const int x_slot = (L.tw * (L.pair ? L.th / 2 + 2 : L.th + 2) * o.bk * 2 + 1023) & ~1023;
-    const int w_bytes = 128 * o.bk * 2;
+    // 32-channel K blocks: one weight stage holds the k-blocks of all three row taps of a column shift (24 KB, 6 MMAs per
+    // barrier round trip instead of 2) - with 2 MMAs per stage the single MMA-issuing thread is the critical path
+    L.ks = (o.bk == 32 && !L.pair && (o.cfg_ks > 0 ? o.cfg_ks == 3 : wgroup_default())) ? 3 : 1;
+    const int w_bytes = L.ks * 128 * o.bk * 2;
     const int staging = (L.tw * L.th * L.gw * (ob.fp32 ? 4 : 2) + 1023) & ~1023;
-    const int budget = 224 * 1024 - staging;
-    L.stg_bufs = 1;
-    L.ks = 1;
+    // residual layers on 32-channel K blocks: a second staging tile lets the next item's residual tile arrive while this
+    // item is multiplied (the small K blocks leave the room); falls back to one tile when the rings would not fit
+    L.stg_bufs = (q.res_buf >= 0 && o.bk == 32 && !L.pair && stg2_default() &&
+                  224 * 1024 - 2 * staging - 2 * x_slot >= (L.ks == 3 ? 2 : 4) * w_bytes) ? 2 : 1;
+    const int budget = 224 * 1024 - L.stg_bufs * staging;
     int xs = o.cfg_xslots > 0 ? o.cfg_xslots : 3;
-    while (xs > 2 && budget - xs * x_slot < 4 * w_bytes) --xs;
+    while (xs > 2 && budget - xs * x_slot < (L.ks == 3 ? 2 : 4) * w_bytes) --xs;
     int ws = (budget - xs * x_slot) / w_bytes;
-    if (ws < 3) return fail(2, "tap-reuse variant does not fit shared memory (tile %dx%d, bk %d)", L.tw, L.th, o.bk);
+    if (ws < (L.ks == 3 ? 2 : 3)) return fail(2, "tap-reuse variant does not fit shared memory (tile %dx%d, bk %d)", L.tw, L.th, o.bk);
     L.xslots = xs;
     // 32-channel K blocks (96-channel layers) have 8 KB weight stages: 8 of them leave half of the shared memory - i.e. of
     // the bytes in flight that hide the L2 latency - unused, so the ring may go 16 deep
@@ -778,12 +795,13 @@ extern "C" int vgh_detector_autotune(vgh_detector* d, int iters, void* stream) {
       }
       for (int ci = 0; ci < n_cand; ++ci) {
         const int ptw = cands[ci].tw, pth = cands[ci].th;
-        for (int xs : {2, 3, 4}) for (int cl = 0; cl <= cluster_default(); ++cl) for (int pr = 0; pr <= pair_default(); ++pr) {
+        for (int xs : {2, 3, 4}) for (int cl = 0; cl <= cluster_default(); ++cl) for (int pr = 0; pr <= pair_default(); ++pr) for (int wg : {1, 3}) {
           if (xs == 4 && (o.bk != 32 || !deep_rings())) continue;   // a fourth pixel slot only fits next to the small 32-channel K blocks
+          if (wg == 3 && (o.bk != 32 || pr || !wgroup_default())) continue;
           OpRt t = o;
-          t.cfg_ks = 1; t.cfg_swap = 1; t.cfg_mt = 0; t.cfg_stages = 0; t.cfg_xr = 1; t.cfg_xslots = xs; t.cfg_cluster = cl; t.cfg_pair = pr;
+          t.cfg_ks = wg; t.cfg_swap = 1; t.cfg_mt = 0; t.cfg_stages = 0; t.cfg_xr = 1; t.cfg_xslots = xs; t.cfg_cluster = cl; t.cfg_pair = pr;
           t.cfg_tw = ptw; t.cfg_th = pth;
-          if (build_conv(d, t) || t.L.xslots != xs || t.L.cluster != cl + 1 || t.L.pair != pr || conv_launch(t.L, t.bk, s)) continue;
+          if (build_conv(d, t) || t.L.xslots != xs || t.L.cluster != cl + 1 || t.L.pair != pr || t.L.ks != wg || conv_launch(t.L, t.bk, s)) continue;
           float ms = 1e30f;
           for (int rep = 0; rep < 2; ++rep) {
             cudaEventRecord(e0, s);
@@ -794,7 +812,7 @@ extern "C" int vgh_detector_autotune(vgh_detector* d, int iters, void* stream) {
             cudaEventElapsedTime(&m, e0, e1);
             if (m < ms) ms = m;
           }
-          if (ms < best) { best = ms; best_swap = 1; best_mt = 1; best_st = 0; best_tw = t.cfg_tw; best_th = t.cfg_th; best_ks = 1; best_xr = 1; best_xs = xs; best_cl = cl; best_pr = pr; }
+          if (ms < best) { best = ms; best_swap = 1; best_mt = 1; best_st = 0; best_tw = t.cfg_tw; best_th = t.cfg_th; best_ks = wg; best_xr = 1; best_xs = xs; best_cl = cl; best_pr = pr; }
         }
       }
     }

@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_flame.py tests/test_gpu_net.py tests/test_gpu_mesh.py -q -x > gpurun_out/r2b_flame_tests.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r2b_flame_tests.log
+timeout 300 python tools/bench_flame.py ${1:-r2b_dmma2} 2>&1 | tail -8
+VGGHEADS_B200_SPARSE_HEADS=1 timeout 600 ncu --profile-from-start off --set full --import-source on --clock-control none --kernel-name-base demangled \
+  -k 'regex:flame_decode_kernel' -c 1 -o gpurun_out/r2b_ncu_full_flame_${1:-dmma2} -f python tools/ncu_target.py 64 untuned > gpurun_out/r2b_ncu_full_flame.log 2>&1; echo "ncu flame rc=$?"
