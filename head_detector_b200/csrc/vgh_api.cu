@@ -817,13 +817,16 @@ extern "C" int vgh_detector_autotune(vgh_detector* d, int iters, void* stream) {
       }
     }
     if (swap_eligible(o.d, d->bufs[o.d.out_buf])) {
-      for (int max_px : {256, 192, 128}) for (int cl = 0; cl <= cluster_default(); ++cl) {  // pixel-tile size trades MMA width against pipeline depth
+      // pixel-tile size trades MMA width against pipeline depth; 32-channel K blocks: three k-blocks per stage as well (two
+      // MMAs per barrier round trip leave the MMA-issuing thread on the critical path)
+      for (int max_px : {256, 192, 128}) for (int cl = 0; cl <= cluster_default(); ++cl) for (int kg : {1, 3}) {
+        if (kg == 3 && (o.bk != 32 || !wgroup_default() || (o.d.ksize * o.d.ksize * (o.d.cin / 32)) % 3)) continue;
         OpRt t = o;
-        t.cfg_ks = 1; t.cfg_xr = 0; t.cfg_cluster = cl; t.cfg_pair = 0;
+        t.cfg_ks = kg; t.cfg_xr = 0; t.cfg_cluster = cl; t.cfg_pair = 0;
         t.cfg_swap = 1; t.cfg_mt = 0; t.cfg_stages = 0;
         pick_tile_swap(o.L.Ho, o.L.Wo, t.cfg_tw, t.cfg_th, max_px);
         if (max_px != 256 && t.cfg_tw * t.cfg_th > max_px) continue;
-        if (build_conv(d, t) || t.L.cluster != cl + 1 || conv_launch(t.L, t.bk, s)) continue;
+        if (build_conv(d, t) || t.L.cluster != cl + 1 || t.L.ks != kg || conv_launch(t.L, t.bk, s)) continue;
         float ms = 1e30f;
         for (int rep = 0; rep < 2; ++rep) {  // best of two timed bursts: the clock / power state is noisy
           cudaEventRecord(e0, s);
