@@ -217,11 +217,15 @@ __global__ void __launch_bounds__(kTileV* HG, HG == 1 ? 4 : 3) flame_decode_kern
 
   // ---- prologue: betas, per-head rotations
   if (fresh) {
-  for (int idx = tid; idx < lb * kHeads; idx += blockDim.x) {
-    const int h = idx / lb, i = idx - h * lb;
+  // (every load below is independent of the previous one and unrolled, so a phase costs ~one L2 round trip: at kernel start
+  // all resident CTAs run this prologue at the same time and nothing else can hide it)
+  for (int i = tid; i < lb; i += blockDim.x) {
     const int l = i < a.ns ? i : 300 + (i - a.ns);
-    const int hg = head0 + h;
-    beta_s[i * kBP + h] = hg < n_heads ? a.params[static_cast<size_t>(hg) * kParams + l] : 0.f;
+    float v[kHeads];
+#pragma unroll
+    for (int h = 0; h < kHeads; ++h) v[h] = head0 + h < n_heads ? __ldg(a.params + static_cast<size_t>(head0 + h) * kParams + l) : 0.f;
+#pragma unroll
+    for (int h = 0; h < kHeads; ++h) beta_s[i * kBP + h] = v[h];
   }
   for (int idx = tid; idx < (lt_pad - lt) * kHeads; idx += blockDim.x) beta_s[(lt + idx / kHeads) * kBP + idx % kHeads] = 0.f;
   if (tid < kHeads) {
@@ -229,12 +233,14 @@ __global__ void __launch_bounds__(kTileV* HG, HG == 1 ? 4 : 3) flame_decode_kern
     float R2[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     float sc = 1.f, t[3] = {0, 0, 0}, xf[3] = {0.f, 0.f, 1.f};
     if (hg < n_heads) {
-      const float* p = a.params + static_cast<size_t>(hg) * kParams;
-      rodrigues_f32(p + 400, R2);
-      rot6d_to_mat(p + 403, R);
-      t[0] = p[409]; t[1] = p[410]; t[2] = p[411];
-      sc = fmaxf(p[412], 1e-8f);
-      if (a.xform) { xf[0] = a.xform[hg * 3]; xf[1] = a.xform[hg * 3 + 1]; xf[2] = a.xform[hg * 3 + 2]; }
+      float q[13];   // jaw (3), rot6d (6), translation (3), scale
+#pragma unroll
+      for (int i = 0; i < 13; ++i) q[i] = __ldg(a.params + static_cast<size_t>(hg) * kParams + 400 + i);
+      if (a.xform) { xf[0] = __ldg(a.xform + hg * 3); xf[1] = __ldg(a.xform + hg * 3 + 1); xf[2] = __ldg(a.xform + hg * 3 + 2); }
+      rodrigues_f32(q, R2);
+      rot6d_to_mat(q + 3, R);
+      t[0] = q[9]; t[1] = q[10]; t[2] = q[11];
+      sc = fmaxf(q[12], 1e-8f);
       if (a.rot)   // (every CTA that starts on this head group writes the same values)
         for (int i = 0; i < 9; ++i) a.rot[static_cast<size_t>(hg) * 9 + i] = R[i];
     }
@@ -249,24 +255,36 @@ __global__ void __launch_bounds__(kTileV* HG, HG == 1 ? 4 : 3) flame_decode_kern
     st_s[tid * 8 + 4] = xf[0]; st_s[tid * 8 + 5] = xf[1]; st_s[tid * 8 + 6] = xf[2];
   }
   __syncthreads();
-  // jaw joint J2 = J2_template + JS2 . beta ; tJ = J2 - R2 . J2.  Four lanes share one (head, coord) dot product so the
-  // 192..400-term chain is four times shorter; the [3][400] regressor x basis table is read straight from L2 (its loads
-  // do not depend on the chain, so they pipeline).
+  // jaw joint J2 = J2_template + JS2 . beta ; tJ = J2 - R2 . J2.  The 3 * kHeads (head, coordinate) dot products of
+  // 192..400 terms are spread over 16-lane groups, three outputs per group; the [3][400] regressor x basis table is read
+  // straight from L2, twelve independent loads per lane in flight.
   {
-    const int o = tid >> 2, part = tid & 3;
-    const bool live = o < kHeads * 3;
-    const int h = live ? o / 3 : 0, k = live ? o - h * 3 : 0;
-    double acc = 0.0;
-    if (live) {
-#pragma unroll 8
-      for (int i = part; i < lb; i += 4) {
+    constexpr int kGroups = 4 * HG * 2;          // 16-lane groups of the CTA: 16 | 8 -> exactly three outputs each
+    static_assert(3 * kGroups == 3 * kHeads, "three (head, coordinate) outputs per 16-lane group");
+    const int g16 = tid >> 4, sub = tid & 15;
+    double a3[3] = {0.0, 0.0, 0.0};
+    for (int i0 = 0; i0 < lb; i0 += 64) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * 16 + sub;
+        const bool ok = i < lb;
         const int l = i < a.ns ? i : 300 + (i - a.ns);
-        acc = fma(__ldg(a.c.js2 + k * kL + l), static_cast<double>(beta_s[i * kBP + h]), acc);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const int o = g16 + j * kGroups, h = o / 3, k = o - h * 3;
+          const double js = ok ? __ldg(a.c.js2 + k * kL + l) : 0.0;
+          const double b = ok ? static_cast<double>(beta_s[i * kBP + h]) : 0.0;
+          a3[j] = fma(js, b, a3[j]);
+        }
       }
     }
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    if (live && part == 0) tj_s[o] = a.c.j2t[k] + acc;  // temporarily J2
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+#pragma unroll
+      for (int sft = 1; sft < 16; sft <<= 1) a3[j] += __shfl_xor_sync(0xffffffffu, a3[j], sft);
+      const int o = g16 + j * kGroups;
+      if (sub == 0) tj_s[o] = a.c.j2t[o % 3] + a3[j];  // temporarily J2
+    }
   }
   __syncthreads();
   if (tid < kHeads) {

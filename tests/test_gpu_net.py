@@ -355,6 +355,38 @@ def test_kernel_variants_every_buffer_small(monkeypatch, swap, xr, cluster, pair
     assert not bad, bad
 
 
+@pytest.mark.parametrize("wgroup,stg2,rings", [("0", "0", "0"), ("1", "0", "1"), ("0", "1", "1")])
+def test_ring_variants_every_buffer_small(monkeypatch, wgroup, stg2, rings):
+    """The 32-channel K blocks of the tap-reuse kernel (96- and 32-channel layers): grouped weight stages (three row taps
+    per stage), the second staging tile with the residual prefetch, deep rings - each switched off in turn (the defaults,
+    all on, are what every other test runs), buffer by buffer against the CPU interpretation."""
+    from head_detector_b200.engine import Engine
+
+    monkeypatch.setenv("VGGHEADS_B200_SWAP", "1")
+    monkeypatch.setenv("VGGHEADS_B200_WGROUP", wgroup)
+    monkeypatch.setenv("VGGHEADS_B200_STG2", stg2)
+    monkeypatch.setenv("VGGHEADS_B200_DEEP_RINGS", rings)
+    S, B = 128, 3
+    eng = Engine(no.synthetic_weights(4), B, S)
+    used = [eng.op_config(i) for i, op in enumerate(eng.plan.ops) if op.kind == 1]
+    assert any(c["mt"] == -3 and c["stages"] >= 100 for c in used) == (wgroup == "1")   # tap reuse with three k-blocks per weight stage
+    torch.manual_seed(1)
+    img = torch.randint(0, 256, (B, S, S, 3), dtype=torch.uint8)
+    eng.forward(img.cuda())
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = pe.run_plan(eng.packed, img, emulate_bf16=True)
+    bad = []
+    tol_max, tol_mean = FLIP_TOL[eng.act_dtype]
+    for name, i in eng.plan.buf_names.items():
+        got, want = eng.read_buffer(name), ref[i]
+        scale = want.abs().max().item() + 1e-6
+        err = (got - want).abs()
+        if not (err.max().item() <= tol_max * scale + 1e-5 and err.mean().item() <= tol_mean * scale):
+            bad.append((name, err.max().item(), err.mean().item(), scale))
+    assert not bad, bad
+
+
 @pytest.mark.parametrize("xr,cluster", [("1", "1"), ("0", "1"), ("1", "0"), ("0", "0")])
 def test_kernel_variants_key_buffers_640(monkeypatch, xr, cluster):
     """Reference resolution with the swapped kernel forced everywhere: 160/80/40/20-pixel maps, tiles that

@@ -17,6 +17,7 @@ for k in e:
     if isinstance(e[k], dict) and "boxes_max_abs_err_px" in e[k]:
         print("  ", k, {kk: (round(vv, 6) if isinstance(vv, float) else vv) for kk, vv in e[k].items() if kk != "stage_rel_err"})
 PY
+timeout 300 python tools/bench_flame.py r2b_final 2>&1 | tail -7
 timeout 600 python tools/profile_ops.py 64 640 r2b_final > gpurun_out/r2b_final_ops.log 2>&1; head -2 gpurun_out/ops_r2b_final.txt
 VGGHEADS_B200_SPARSE_HEADS=1 timeout 900 ncu --profile-from-start off --clock-control none --csv \
   --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__cycles_active.avg,sm__cycles_elapsed.avg,l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed,lts__t_bytes.sum \
