@@ -142,3 +142,30 @@ def test_sparse_heads_plan_equals_dense_plan_at_survivors():
         for pi, (b, y, x) in enumerate(patches[l]):
             want, have = fd[b, y, x], fs[0, pi * arch.PATCH + arch.PATCH_C, arch.PATCH_C]
             assert (want - have).abs().max().item() <= 1e-5 * max(1.0, want.abs().max().item()), (l, b, y, x)
+
+
+def test_act_dtype_selection_and_fp16_range_check(monkeypatch):
+    """Storage format of the throughput mode: fp16 by default, $VGGHEADS_B200_ACT selects, anything else is
+    refused; packing refuses weights that do not fit fp16 instead of writing infinities; the fp16 pack is the closer one."""
+    monkeypatch.delenv("VGGHEADS_B200_ACT", raising=False)
+    assert arch.default_act_dtype() == "fp16"
+    monkeypatch.setenv("VGGHEADS_B200_ACT", "bf16")
+    assert arch.default_act_dtype() == "bf16"
+    monkeypatch.setenv("VGGHEADS_B200_ACT", "fp8")
+    with pytest.raises(ValueError):
+        arch.default_act_dtype()
+    w = no.synthetic_weights(3)
+    packs = {dt: arch.pack(arch.build_plan(64, act_dtype=dt), w) for dt in ("bf16", "fp16")}
+    assert packs["bf16"].weights.shape == packs["fp16"].weights.shape and (packs["bf16"].bias == packs["fp16"].bias).all()
+    m = packs["fp16"].op_meta[1]
+    sl = slice(m["w_off"], m["w_off"] + m["n_pad"] * m["k_total"])
+    ref = torch.from_numpy(packs["bf16"].weights[sl].view(np.int16).copy()).view(torch.bfloat16).double()
+    got = torch.from_numpy(packs["fp16"].weights[sl].view(np.int16).copy()).view(torch.float16).double()
+    assert (ref - got).abs().max() <= 2.0 ** -8 * ref.abs().max()          # the same matrix, each within its own rounding
+    big = dict(w)
+    big["stage1.down.w"] = w["stage1.down.w"] * 1e6
+    arch.pack(arch.build_plan(64, act_dtype="bf16"), big)                  # fits bf16's range
+    with pytest.raises(ValueError, match="fp16"):
+        arch.pack(arch.build_plan(64, act_dtype="fp16"), big)
+    with pytest.raises(AssertionError):
+        arch.split_plan(arch.build_plan(64, act_dtype="fp16", fused_stem=False))   # the parity mode splits into bf16 terms
