@@ -116,7 +116,8 @@ def test_product_fold_matches_oracle_fold_and_unfused_forward():
         arch.deploy_from_unfused(bad)
 
 
-def test_sparse_heads_plan_equals_dense_plan_at_survivors():
+@pytest.mark.parametrize("act_dtype", ["fp16", "bf16"])
+def test_sparse_heads_plan_equals_dense_plan_at_survivors(act_dtype):
     """Two-phase plan (FLAME branch on 8x8 survivor patches after NMS) against the dense plan, both interpreted
     on the CPU: identical raw FLAME rows at the survivors - interior anchors, anchors on the image border / in
     the corners (the patch mask reproduces the dense graph's zero padding layer by layer) and vertically stacked
@@ -126,8 +127,8 @@ def test_sparse_heads_plan_equals_dense_plan_at_survivors():
 
     S, B, K = 128, 2, 6
     w = no.synthetic_weights(3)
-    dense = arch.pack(arch.build_plan(S), w)
-    sparse = arch.pack(arch.build_plan(S, sparse_heads=(B, K)), w)
+    dense = arch.pack(arch.build_plan(S, act_dtype=act_dtype), w)
+    sparse = arch.pack(arch.build_plan(S, sparse_heads=(B, K), act_dtype=act_dtype), w)
     assert sparse.plan.n_dense_ops is not None and all(op.level > 0 for op in sparse.plan.ops[sparse.plan.n_dense_ops:])
     assert all(op.level == 0 for op in sparse.plan.ops[:sparse.plan.n_dense_ops])
     torch.manual_seed(0)
